@@ -1,0 +1,184 @@
+"""CPU restatement ("port") of the Python half of the PTT hot path.  TEST INFRASTRUCTURE.
+
+The reference is Python and cannot travel to the GPU box, so the checker there is this port:
+plain PyTorch CPU code over the C ops of oracle/pointnet2_ref.c, written as functions of a
+state_dict whose keys are the reference's own (so a reference checkpoint drives it unchanged).
+It is PINNED in this container against the reference's modules imported from /root/reference
+(tests/test_oracle_vs_reference.py) and against the committed golden fixtures the reference
+produced (tests/golden/*.npz, made by tests/golden/make_golden.py).
+
+Citations are file:line under /root/reference/ptt/models/.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import cops
+
+
+def _sub(sd, prefix):
+    n = len(prefix)
+    return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+# ----------------------------------------------------------------------------------------------
+# a5  QueryAndGroup.forward            backbones_3d/pointnet2/pointnet2_utils.py:320-380
+# ----------------------------------------------------------------------------------------------
+def query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True, normalize_xyz=False):
+    """xyz (B,N,3), new_xyz (B,M,3), features (B,C,N)|None -> new_features (B,3+C,M,ns), grouped_xyz, idx."""
+    idx = cops.ball_query(new_xyz.contiguous(), xyz.contiguous(), float(radius), int(nsample))  # :337
+    grouped_xyz = cops.group_points(xyz.transpose(1, 2).contiguous(), idx)                     # :350-351
+    grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)                           # :352
+    if normalize_xyz:
+        grouped_xyz = grouped_xyz / radius                                                       # :353-354
+    if features is not None:
+        grouped = cops.group_points(features.contiguous(), idx)                                 # :357
+        new_features = torch.cat([grouped_xyz, grouped], dim=1) if use_xyz else grouped         # :358-363
+    else:
+        new_features = grouped_xyz                                                              # :364-368
+    return new_features, grouped_xyz, idx
+
+
+# ----------------------------------------------------------------------------------------------
+# a7  SharedMLP = [1x1 Conv2d(no bias) -> BatchNorm2d -> ReLU] * L    pytorch_utils.py:12-36,158-189
+# ----------------------------------------------------------------------------------------------
+def shared_mlp(sd, x, training=False, momentum=0.1, eps=1e-5):
+    """sd keys: layer{i}.conv.weight, layer{i}.normlayer.bn.{weight,bias,running_mean,running_var}."""
+    i = 0
+    while "layer%d.conv.weight" % i in sd:
+        p = "layer%d." % i
+        x = F.conv2d(x, sd[p + "conv.weight"], sd.get(p + "conv.bias"))
+        if p + "normlayer.bn.weight" in sd:
+            x = F.batch_norm(x, sd[p + "normlayer.bn.running_mean"], sd[p + "normlayer.bn.running_var"],
+                             sd[p + "normlayer.bn.weight"], sd[p + "normlayer.bn.bias"],
+                             training=training, momentum=momentum, eps=eps)
+        x = F.relu(x)
+        i += 1
+    return x
+
+
+# ----------------------------------------------------------------------------------------------
+# a6  PointnetSAModuleVotes.forward    backbones_3d/pointnet2/pointnet2_modules.py:57-90
+# ----------------------------------------------------------------------------------------------
+def sa_module_votes(sd, xyz, features, npoint, radius, nsample, sample_method="fps", use_xyz=True,
+                    normalize_xyz=False, inds=None, training=False):
+    """-> new_xyz (B,npoint,3), new_features (B,Cout,npoint), inds int64 (B,npoint)."""
+    B = xyz.shape[0]
+    if inds is None:
+        if sample_method == "fps":
+            inds = cops.furthest_point_sampling(xyz.contiguous(), npoint)                       # :72-73
+        elif sample_method in ("sequence", "rs"):
+            inds = torch.arange(npoint, dtype=torch.int32).repeat(B, 1)                          # :68-71
+        else:
+            raise NotImplementedError(sample_method)
+    new_xyz = cops.gather_points(xyz.transpose(1, 2).contiguous(), inds.int().contiguous())     # :79
+    new_xyz = new_xyz.transpose(1, 2).contiguous()                                              # :81
+    grouped, _, _ = query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz, normalize_xyz)  # :83
+    y = shared_mlp(_sub(sd, "mlp_module."), grouped, training=training)                         # :84
+    y = y.max(dim=3)[0]                                                                          # :85-88
+    return new_xyz, y, inds.to(torch.int64)                                                      # :90
+
+
+# ----------------------------------------------------------------------------------------------
+# a8  PointNet2BackboneLight.branch_forward    backbones_3d/pointnet2_backbone.py:41-50
+# ----------------------------------------------------------------------------------------------
+def backbone_branch(sd, pts, npoints, radii=(0.3, 0.5, 0.7), nsamples=(32, 32, 32),
+                    sample_methods=("fps", "sequence", "sequence"), normalize_xyz=True, training=False):
+    """pts (B,N,3) -> seeds (B,n3,3), point_features (B,256,n3), inds int64 (B,n3)."""
+    xyz, feats = pts[..., 0:3].contiguous(), None
+    inds = []
+    for l in range(3):
+        xyz, feats, i = sa_module_votes(_sub(sd, "SA_modules.%d." % l), xyz, feats, npoints[l], radii[l],
+                                        nsamples[l], sample_methods[l], True, normalize_xyz,
+                                        training=training)
+        inds.append(i)
+    point_features = F.conv1d(feats, sd["cov_final.weight"], sd["cov_final.bias"])              # :46
+    composed = inds[0].gather(1, inds[1]).gather(1, inds[2])                                    # :48
+    return xyz, point_features, composed
+
+
+# ----------------------------------------------------------------------------------------------
+# a9  TransformerBlock.forward (kNN vector attention)    transformer_block/variants.py:127-165
+# ----------------------------------------------------------------------------------------------
+def _gather_rows(points, idx):
+    """index_points (model_utils/layer_utils.py:29-40): points (B,N,C), idx (B,S,K) -> (B,S,K,C)."""
+    B, S, K = idx.shape
+    flat = idx.reshape(B, S * K, 1).expand(-1, -1, points.shape[-1])
+    return torch.gather(points, 1, flat).reshape(B, S, K, -1)
+
+
+def _linear(sd, name, x):
+    return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
+
+
+def _mlp2(sd, name, x):
+    return _linear(sd, name + ".2", F.relu(_linear(sd, name + ".0", x)))
+
+
+def knn_indices(xyz, k):
+    """argsort of square_distance (layer_utils.py:12-26, variants.py:150-151) with ties resolved
+    lowest-index-first (the reference's argsort is unstable, so its tie order is unspecified)."""
+    return cops.knn(xyz.contiguous(), int(k)).to(torch.int64)
+
+
+def transformer_block(sd, xyz, features, k, variant="TransformerBlock", knn_idx=None):
+    """xyz (B,n,3), features (B,n,d_points) -> (res (B,n,d_points), attn (B,n,k,d_model)).
+
+    variant: 'TransformerBlock' (variants.py:127-165), 'TransformerBlockMLP' (:211-256, two-layer
+    fc1/fc2), 'TransformerBlockOffset' (:297-334, fc2(x - res))."""
+    if knn_idx is None:
+        knn_idx = knn_indices(xyz, k)                                                            # :150-151
+    knn_xyz = _gather_rows(xyz, knn_idx)                                                          # :152
+    pre = features
+    x = _mlp2(sd, "fc1", features) if variant == "TransformerBlockMLP" else _linear(sd, "fc1", features)  # :155
+    q = _linear(sd, "w_qs", x)
+    kk = _gather_rows(_linear(sd, "w_ks", x), knn_idx)
+    v = _gather_rows(_linear(sd, "w_vs", x), knn_idx)                                             # :156
+    pos = _mlp2(sd, "fc_delta", xyz[:, :, None] - knn_xyz)                                        # :158
+    attn = _mlp2(sd, "fc_gamma", q[:, :, None] - kk + pos)                                        # :160
+    attn = F.softmax(attn / math.sqrt(kk.size(-1)), dim=-2)                                       # :161
+    res = torch.einsum("bmnf,bmnf->bmf", attn, v + pos)                                           # :163
+    if variant == "TransformerBlockOffset":
+        res = x - res
+    res = (_mlp2(sd, "fc2", res) if variant == "TransformerBlockMLP" else _linear(sd, "fc2", res)) + pre  # :164
+    return res, attn
+
+
+# a10 TransformerBlockSTD.forward (dense n x n dot-product attention)    variants.py:12-40
+def transformer_block_std(sd, xyz, features):
+    pre = features
+    x = _linear(sd, "fc1", features)
+    q, k, v = _linear(sd, "w_qs", x), _linear(sd, "w_ks", x), _linear(sd, "w_vs", x)
+    attn = F.softmax(q @ k.transpose(1, 2) / math.sqrt(k.size(-1)), dim=-1)
+    res = attn @ (v + _mlp2(sd, "fc_delta", xyz))
+    return _linear(sd, "fc2", res) + pre, attn
+
+
+# ----------------------------------------------------------------------------------------------
+# The bench / smoke "frame": the hot-path functions a1-a9 in dependency order, with the non-hot
+# modules between them (CosineSimAug, the heads' Conv1d stacks -- SURVEY.md 8(f) N1/N2) replaced by
+# fixed cheap glue so that real tensors flow from one hot stage into the next:
+#   search/template clouds -> backbone (SA1-3 x 2 branches)                    pointnet2_backbone.py:52-67
+#   centroid-head transformer on (search_seeds, search_feats^T)                centroids_voting_head.py:71-76
+#   box-head SA on (votes = search_seeds, votes_feats = [score=0.5 | feats])   box_voting_head.py:75-79
+#   box-head transformer on (centres, proposal_feats^T)                        box_voting_head.py:81-86
+# ptt_b200.hotpath.HotPath.forward is the product twin of this function.
+# ----------------------------------------------------------------------------------------------
+def hot_path_frame(sd, search, template, cfg=None):
+    c = dict(npoints_search=(512, 256, 128), npoints_template=(256, 128, 64), radii=(0.3, 0.5, 0.7),
+             nsamples=(32, 32, 32), knn=16, box_npoint=64, box_radius=0.3, box_nsample=16)
+    c.update(cfg or {})
+    bb = _sub(sd, "backbone_3d.")
+    s_xyz, s_feat, s_inds = backbone_branch(bb, search, c["npoints_search"], c["radii"], c["nsamples"])
+    t_xyz, t_feat, t_inds = backbone_branch(bb, template, c["npoints_template"], c["radii"], c["nsamples"])
+    cen, _ = transformer_block(_sub(sd, "centroid_voting_head.transformer_block."), s_xyz,
+                               s_feat.transpose(1, 2).contiguous(), c["knn"])
+    votes_feats = torch.cat([torch.full_like(cen[:, :, :1], 0.5), cen], dim=2).transpose(1, 2).contiguous()
+    b_xyz, b_feat, _ = sa_module_votes(_sub(sd, "box_voting_head.vote_aggregation."), s_xyz, votes_feats,
+                                       c["box_npoint"], c["box_radius"], c["box_nsample"], "fps", True, True)
+    box, _ = transformer_block(_sub(sd, "box_voting_head.transformer_block."), b_xyz,
+                               b_feat.transpose(1, 2).contiguous(), c["knn"])
+    return {"search_seeds": s_xyz, "search_feats": s_feat, "search_inds": s_inds,
+            "template_seeds": t_xyz, "template_feats": t_feat, "template_inds": t_inds,
+            "centroid_feats": cen, "box_centers": b_xyz, "box_sa_feats": b_feat, "box_feats": box}
