@@ -1,0 +1,38 @@
+// Shared helpers for the sm_100a kernels of libptt_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptt_b200.h"
+
+#define PTT_CHECK_ARG(cond)                      \
+  do {                                           \
+    if (!(cond)) return PTT_ERR_INVALID_ARGUMENT; \
+  } while (0)
+
+// Returns the launch error (if any) of the kernels enqueued so far by this call, without syncing.
+static inline int ptt_launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PTT_OK : (int)e;
+}
+
+static inline cudaStream_t as_stream(ptt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// a*a + b*b + c*c exactly as nvcc's default contraction emits it for upstream pointnet2_ops
+// (oracle/probe_contraction.sh): FMUL on the middle term, then two FFMAs.  Written with intrinsics
+// so the result does not depend on how the compiler feels about this translation unit.
+__device__ __forceinline__ float sq3(float a, float b, float c) {
+  return __fmaf_rn(c, c, __fmaf_rn(a, a, __fmul_rn(b, b)));
+}
+
+// layer_utils.square_distance (layer_utils.py:26): ((dx*dx + dy*dy) + dz*dz), every step rounded.
+__device__ __forceinline__ float sq3_nofma(float a, float b, float c) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c));
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
