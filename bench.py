@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the PTT point-feature hot path (SA stack + transformer blocks) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (ptt_b200.hotpath.HotPath: backbone SA1-3 on the search and template
+clouds + cov_final, centroid-head transformer block, box-head SA, box-head transformer block) over one batch of
+synthetic frames.  Workload = BASELINE.json configs[1]: KITTI Car ptt.yaml, N=1024 search / 512 template points,
+batch 48 per GPU (weak scaling: every rank processes its own 48 frames; no data-path collective).
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM, device-timed.  `e2e`: through the host API
+(HotPath.forward_host) with pinned host buffers, H2D + D2H inside the timed region.  `roofline`: the dominant
+stage, algorithmic FLOPs / CUDA-event time on its stream.  `cpu_baseline`: the CPU oracle port on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "tracked frames/sec (SA + transformer hot path, forward)"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=48, help="frames per GPU per step")
+    ap.add_argument("--nsearch", type=int, default=1024)
+    ap.add_argument("--ntemplate", type=int, default=512)
+    ap.add_argument("--kind", default="dense", choices=["dense", "sparse"])
+    ap.add_argument("--cpu-frames", type=int, default=4, help="frames per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {"workload": "KITTI Car ptt.yaml hot path: N=%d search + %d template pts, batch %d per GPU, %s synthetic crops"
+                        % (a.nsearch, a.ntemplate, a.batch, a.kind),
+            "global_batch": a.batch * n_gpus, "batch_per_gpu": a.batch, "n_search": a.nsearch, "n_template": a.ntemplate,
+            "mode": "eval (BatchNorm folded), forward", "parallelism": "batch-sharded replicas x%d, no collective" % n_gpus,
+            "l2": "flushed between timed steps (256 MiB write outside the event brackets)"}
+
+
+def scaled_cfg(a):
+    n = a.nsearch
+    if n == 1024 and a.ntemplate == 512:
+        return None
+    # NPOINTS scale with N (reproduces the yaml at N = 1024)
+    nt = a.ntemplate
+    return dict(npoints_search=(n // 2, n // 4, n // 8), npoints_template=(nt // 2, nt // 4, nt // 8))
+
+
+# per-frame algorithmic work of the hot path (DESIGN.md "Measurement")
+def algorithmic(a):
+    cfgs = scaled_cfg(a) or dict(npoints_search=(512, 256, 128), npoints_template=(256, 128, 64))
+    specs = ([3, 64, 64, 128], [131, 128, 128, 256], [259, 128, 128, 256])
+
+    def mlp_macs(spec):
+        return sum(spec[i] * spec[i + 1] for i in range(len(spec) - 1))
+
+    flops = {}
+    for tag, npts in (("search", cfgs["npoints_search"]), ("template", cfgs["npoints_template"])):
+        for l in range(3):
+            flops["%s.sa%d.mlp" % (tag, l + 1)] = 2.0 * npts[l] * 32 * mlp_macs(specs[l])
+    flops["box.sa.mlp"] = 2.0 * 64 * 16 * mlp_macs([260, 256, 256, 256])
+
+    def tr(n, k=16, dp=256, dm=512):
+        return 2.0 * (n * dp * dm + 3 * n * dm * dm + n * k * (3 * dm + dm * dm) + 2 * n * k * dm * dm + n * dm * dp)
+
+    flops["centroid.transformer"] = tr(cfgs["npoints_search"][2])
+    flops["box.transformer"] = tr(64)
+    return flops
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.error = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                     "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+            while not self._halt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing: report it, do not fail the bench
+            self.error = repr(e)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s), **({"error": self.error} if self.error else {})}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def cpu_hot_path(a, frames, threads, steps, warmup):
+    """The reference's CPU path for the hot path = oracle.torch_port (PyTorch CPU + C ops), timed on host cores."""
+    import torch
+
+    from oracle import torch_port
+    from ptt_b200 import synth
+
+    torch.set_num_threads(threads)
+    sd = synth.hot_path_state_dict(0)
+    search = torch.from_numpy(synth.make_clouds(frames, a.nsearch, 900, a.kind))
+    template = torch.from_numpy(synth.make_clouds(frames, a.ntemplate, 901, a.kind, role="template"))
+    cfg = scaled_cfg(a)
+    with torch.no_grad():
+        for _ in range(warmup):
+            torch_port.hot_path_frame(sd, search, template, cfg)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            torch_port.hot_path_frame(sd, search, template, cfg)
+        dt = time.perf_counter() - t0
+    return frames * steps / dt, dt / steps
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    threads = os.cpu_count() or 1
+    frames = a.cpu_frames
+    steps, warmup = max(1, min(a.steps, 10)), max(1, min(a.warmup, 2))
+    fps, sec = cpu_hot_path(a, frames, threads, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d frames per step x %d steps (the reference is Python over a CUDA-only "
+                                       "third-party extension; its CPU path is the oracle port, oracle/torch_port.py "
+                                       "over oracle/pointnet2_ref.c)" % (frames, steps)},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    from ptt_b200 import _lib, hotpath, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    hp = hotpath.HotPath(synth.hot_path_state_dict(0), cfg=scaled_cfg(a), device=dev)
+    B = a.batch
+    # each rank owns its own shard of the global batch (distinct seeds): rank r gets frames [r*B, (r+1)*B)
+    n_sets = 4
+    search_h = [torch.from_numpy(synth.make_clouds(B, a.nsearch, 1000 + 16 * rank + i, a.kind)).pin_memory() for i in range(n_sets)]
+    templ_h = [torch.from_numpy(synth.make_clouds(B, a.ntemplate, 2000 + 16 * rank + i, a.kind, role="template")).pin_memory()
+               for i in range(n_sets)]
+    search_d = [x.to(dev) for x in search_h]
+    templ_d = [x.to(dev) for x in templ_h]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(i):
+        return hp(search_d[i % n_sets], templ_d[i % n_sets])
+
+    for i in range(a.warmup):
+        step(i)
+    barrier()
+
+    # ---- device-resident timed region: K steps, each bracketed by events, L2 flushed between steps ----
+    hp.profile(True)
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    launches0 = _lib.launch_count()
+    ev = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(a.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(i)
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    stage_ms = hp.stage_ms()
+    hp.profile(False)
+    dev_ms = sum(x.elapsed_time(y) for x, y in ev)
+
+    # ---- end-to-end through the host API: pinned host in, pinned host out, copies inside the timed region ----
+    for i in range(max(2, a.warmup // 2)):
+        hp.forward_host(search_h[i % n_sets], templ_h[i % n_sets])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        out_h = hp.forward_host(search_h[i % n_sets], templ_h[i % n_sets])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = search_h[0].numel() * 4 + templ_h[0].numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in out_h.values())
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3, t_wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, wall_ms = [float(x) for x in times.tolist()]
+
+    if rank == 0:
+        frames = B * n_gpus * a.steps
+        alg = algorithmic(a)
+        # dominant stage = the one with the most time per step
+        known = {k: v for k, v in stage_ms.items() if k in alg}
+        top = max(known, key=known.get)
+        peaks = {}
+        pk = os.path.join(REPO, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        achieved_tf = alg[top] * B / (known[top] * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, n_gpus),
+            "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": top, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
+                         "flops_per_launch": alg[top] * B, "ms_per_launch": known[top]},
+            "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
+            "wall_ms_per_step_incl_flush": wall_ms / a.steps,
+        }
+        if not a.no_cpu_baseline and world == 1:
+            cpu_threads = os.cpu_count() or 1
+            fps, sec = cpu_hot_path(a, a.cpu_frames, cpu_threads, steps=3, warmup=1)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                                    "sample": "%d frames per step x 3 steps of the same workload, oracle/torch_port.py "
+                                              "over oracle/pointnet2_ref.c" % a.cpu_frames}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

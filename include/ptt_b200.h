@@ -27,6 +27,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define PTT_API __attribute__((visibility("default")))
+#else
+#define PTT_API
+#endif
+
 #define PTT_OK 0
 #define PTT_ERR_INVALID_ARGUMENT (-1) /* null pointer, negative size, npoint > N ... */
 #define PTT_ERR_UNSUPPORTED (-2)      /* shape outside what the kernel family covers  */
@@ -35,9 +41,13 @@ extern "C" {
 typedef void* ptt_stream_t; /* cudaStream_t */
 
 /* "ptt_b200 <version> sm_100a" */
-const char* ptt_version(void);
+PTT_API const char* ptt_version(void);
 /* Text for a return code of any function below (static storage). */
-const char* ptt_error_string(int code);
+PTT_API const char* ptt_error_string(int code);
+
+/* Number of kernels this library has launched in this process so far (monotonic; diagnostics only --
+ * the one piece of process-wide state in the library). */
+PTT_API unsigned long long ptt_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * a1  _ext.furthest_point_sampling(xyz, npoint)                     pointnet2_utils.py:78
@@ -46,58 +56,58 @@ const char* ptt_error_string(int code);
  *     new_xyz (B,npoint,3), if not NULL, receives xyz[idx] (fuses _ext.gather_points of
  *     pointnet2_modules.py:79-81).  Workspace is only needed for N > 16384.
  * ------------------------------------------------------------------------------------------- */
-size_t ptt_furthest_point_sampling_workspace_bytes(int B, int N, int npoint);
-int ptt_furthest_point_sampling(const float* xyz, int B, int N, int npoint, int* idx, float* new_xyz,
+PTT_API size_t ptt_furthest_point_sampling_workspace_bytes(int B, int N, int npoint);
+PTT_API int ptt_furthest_point_sampling(const float* xyz, int B, int N, int npoint, int* idx, float* new_xyz,
                                 void* workspace, size_t workspace_bytes, ptt_stream_t stream);
 
 /*     _ext.furthest_point_sampling_with_dist(dist, npoint)          pointnet2_utils.py:48
  *     dist (B,N,N) -> idx (B,npoint).  ('ffps' sampling; dead in the shipped configs.) */
-size_t ptt_furthest_point_sampling_with_dist_workspace_bytes(int B, int N, int npoint);
-int ptt_furthest_point_sampling_with_dist(const float* dist, int B, int N, int npoint, int* idx,
+PTT_API size_t ptt_furthest_point_sampling_with_dist_workspace_bytes(int B, int N, int npoint);
+PTT_API int ptt_furthest_point_sampling_with_dist(const float* dist, int B, int N, int npoint, int* idx,
                                           void* workspace, size_t workspace_bytes, ptt_stream_t stream);
 
 /* a2  _ext.gather_points(points, idx)                                pointnet2_utils.py:112
  *     points (B,C,N), idx (B,M) -> out (B,C,M) */
-int ptt_gather_points(const float* points, const int* idx, int B, int C, int N, int M, float* out,
+PTT_API int ptt_gather_points(const float* points, const int* idx, int B, int C, int N, int M, float* out,
                       ptt_stream_t stream);
 /*     _ext.gather_points_grad(grad_out, idx, N)                      pointnet2_utils.py:118
  *     grad_out (B,C,M), idx (B,M) -> grad_points (B,C,N), zero-filled here then scatter-added */
-int ptt_gather_points_grad(const float* grad_out, const int* idx, int B, int C, int N, int M,
+PTT_API int ptt_gather_points_grad(const float* grad_out, const int* idx, int B, int C, int N, int M,
                            float* grad_points, ptt_stream_t stream);
 
 /* a3  _ext.ball_query(new_xyz, xyz, radius, nsample)                 pointnet2_utils.py:287
  *     new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample) int32: the first nsample k (ascending) with
  *     d2 < radius^2 (fp32), tail padded with the first hit, all-zero row when there is none. */
-int ptt_ball_query(const float* new_xyz, const float* xyz, int B, int N, int M, float radius,
+PTT_API int ptt_ball_query(const float* new_xyz, const float* xyz, int B, int N, int M, float radius,
                    int nsample, int* idx, ptt_stream_t stream);
 
 /* a4  _ext.group_points(points, idx)                                 pointnet2_utils.py:237
  *     points (B,C,N), idx (B,M,K) -> out (B,C,M,K) */
-int ptt_group_points(const float* points, const int* idx, int B, int C, int N, int M, int K,
+PTT_API int ptt_group_points(const float* points, const int* idx, int B, int C, int N, int M, int K,
                      float* out, ptt_stream_t stream);
 /*     _ext.group_points_grad(grad_out, idx, N)                       pointnet2_utils.py:257
  *     grad_out (B,C,M,K) -> grad_points (B,C,N), zero-filled here then scatter-added */
-int ptt_group_points_grad(const float* grad_out, const int* idx, int B, int C, int N, int M, int K,
+PTT_API int ptt_group_points_grad(const float* grad_out, const int* idx, int B, int C, int N, int M, int K,
                           float* grad_points, ptt_stream_t stream);
 
 /*     _ext.three_nn(unknown, known)                                  pointnet2_utils.py:145
  *     unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) (SQUARED distances), idx (B,n,3) */
-int ptt_three_nn(const float* unknown, const float* known, int B, int n, int m, float* dist2, int* idx,
+PTT_API int ptt_three_nn(const float* unknown, const float* known, int B, int n, int m, float* dist2, int* idx,
                  ptt_stream_t stream);
 /*     _ext.three_interpolate(points, idx, weight)                    pointnet2_utils.py:182
  *     points (B,c,m), idx (B,n,3), weight (B,n,3) -> out (B,c,n) */
-int ptt_three_interpolate(const float* points, const int* idx, const float* weight, int B, int c, int m,
+PTT_API int ptt_three_interpolate(const float* points, const int* idx, const float* weight, int B, int c, int m,
                           int n, float* out, ptt_stream_t stream);
 /*     _ext.three_interpolate_grad(grad_out, idx, weight, m)          pointnet2_utils.py:204 */
-int ptt_three_interpolate_grad(const float* grad_out, const int* idx, const float* weight, int B, int c,
+PTT_API int ptt_three_interpolate_grad(const float* grad_out, const int* idx, const float* weight, int B, int c,
                                int n, int m, float* grad_points, ptt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layout helpers for the fused path (point-major activations).
  *   channel-major (B,C,N)  <->  point-major (B,N,ld) with ld >= C (padding columns written as 0)
  * ------------------------------------------------------------------------------------------- */
-int ptt_cm_to_pm(const float* src_cm, int B, int C, int N, float* dst_pm, int ld, ptt_stream_t stream);
-int ptt_pm_to_cm(const float* src_pm, int ld, int B, int C, int N, float* dst_cm, ptt_stream_t stream);
+PTT_API int ptt_cm_to_pm(const float* src_cm, int B, int C, int N, float* dst_pm, int ld, ptt_stream_t stream);
+PTT_API int ptt_pm_to_cm(const float* src_pm, int ld, int B, int C, int N, float* dst_cm, ptt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a5-a7  QueryAndGroup + SharedMLP + max-pool of one set-abstraction layer, eval mode
@@ -116,12 +126,12 @@ int ptt_pm_to_cm(const float* src_pm, int ld, int B, int C, int N, float* dst_cm
 /* Packing: weights[l] is the conv weight (dims[l+1], dims[l]) row-major with input channels in the
  * REFERENCE order [xyz(3) | feats(C)] (QueryAndGroup's cat, pointnet2_utils.py:359); scale/shift
  * (dims[l+1]).  h_* arrays of n_layers DEVICE pointers live on the host. */
-size_t ptt_sa_params_floats(int C, int n_layers, const int* h_dims);
-int ptt_sa_pack_params(int C, int n_layers, const int* h_dims, const float* const* h_weights,
+PTT_API size_t ptt_sa_params_floats(int C, int n_layers, const int* h_dims);
+PTT_API int ptt_sa_pack_params(int C, int n_layers, const int* h_dims, const float* const* h_weights,
                        const float* const* h_scale, const float* const* h_shift, float* params,
                        ptt_stream_t stream);
-size_t ptt_sa_mlp_workspace_bytes(int B, int M, int ns, int C, int n_layers, const int* h_dims);
-int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, const float* new_xyz, const int* idx,
+PTT_API size_t ptt_sa_mlp_workspace_bytes(int B, int M, int ns, int C, int n_layers, const int* h_dims);
+PTT_API int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, const float* new_xyz, const int* idx,
                    int B, int N, int M, int ns, int C, float radius, int normalize_xyz, int n_layers,
                    const int* h_dims, const float* params, float* out_pm, int ld_out, float* out_cm,
                    void* workspace, size_t workspace_bytes, ptt_stream_t stream);
@@ -132,14 +142,14 @@ int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, const float* n
  *   knn: xyz (B,n,3) -> knn_idx (B,n,k): the k nearest (self included) by the fp32 squared distance
  *   of layer_utils.square_distance (layer_utils.py:26), ascending, ties lowest index first.
  * ------------------------------------------------------------------------------------------- */
-int ptt_knn(const float* xyz, int B, int n, int k, int* knn_idx, ptt_stream_t stream);
+PTT_API int ptt_knn(const float* xyz, int B, int n, int k, int* knn_idx, ptt_stream_t stream);
 
 /*   y (R,ldy)[:, 0:Cout] = act( x (R,ldx)[:, 0:K] . W^T + bias ) (+ residual (R,ldr))
  *   wt: packed transposed weight from ptt_linear_pack (nn.Linear weight (Cout,K) -> (Kp,Cp) image). */
-size_t ptt_linear_params_floats(int K, int Cout);
-int ptt_linear_pack(const float* weight, const float* bias, int K, int Cout, float* params,
+PTT_API size_t ptt_linear_params_floats(int K, int Cout);
+PTT_API int ptt_linear_pack(const float* weight, const float* bias, int K, int Cout, float* params,
                     ptt_stream_t stream);
-int ptt_linear_fwd(const float* x, int ldx, int R, int K, const float* params, int Cout, int relu,
+PTT_API int ptt_linear_fwd(const float* x, int ldx, int R, int K, const float* params, int Cout, int relu,
                    const float* residual, int ldr, float* y, int ldy, ptt_stream_t stream);
 
 /*   Whole block.  features (B,n,d_points) -> out (B,n,d_points); attn (B,n,k,d_model) or NULL.
@@ -147,15 +157,15 @@ int ptt_linear_fwd(const float* x, int ldx, int R, int K, const float* params, i
  *   fc1.{weight,bias}, fc2.{weight,bias}, fc_delta.{0,2}.{weight,bias}, fc_gamma.{0,2}.{weight,bias},
  *   w_qs.weight, w_ks.weight, w_vs.weight (nn.Linear layout (out,in)).
  *   variant: 0 = TransformerBlock, 1 = TransformerBlockOffset (fc2(x - res), variants.py:333). */
-size_t ptt_transformer_params_floats(int d_points, int d_model);
-int ptt_transformer_pack_params(int d_points, int d_model, const float* fc1_w, const float* fc1_b,
+PTT_API size_t ptt_transformer_params_floats(int d_points, int d_model);
+PTT_API int ptt_transformer_pack_params(int d_points, int d_model, const float* fc1_w, const float* fc1_b,
                                 const float* fc2_w, const float* fc2_b, const float* delta0_w,
                                 const float* delta0_b, const float* delta2_w, const float* delta2_b,
                                 const float* gamma0_w, const float* gamma0_b, const float* gamma2_w,
                                 const float* gamma2_b, const float* wq, const float* wk, const float* wv,
                                 float* params, ptt_stream_t stream);
-size_t ptt_transformer_block_workspace_bytes(int B, int n, int k, int d_points, int d_model);
-int ptt_transformer_block_fwd(const float* xyz, const float* features, int B, int n, int k, int d_points,
+PTT_API size_t ptt_transformer_block_workspace_bytes(int B, int n, int k, int d_points, int d_model);
+PTT_API int ptt_transformer_block_fwd(const float* xyz, const float* features, int B, int n, int k, int d_points,
                               int d_model, int variant, const float* params, const int* knn_idx_or_null,
                               float* out, float* attn_or_null, void* workspace, size_t workspace_bytes,
                               ptt_stream_t stream);

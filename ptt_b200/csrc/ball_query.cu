@@ -79,9 +79,9 @@ extern "C" int ptt_ball_query(const float* new_xyz, const float* xyz, int B, int
       cudaError_t e = cudaFuncSetAttribute(ball_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    ball_query_kernel<true><<<grid, BQ_WARPS * 32, smem, st>>>(new_xyz, xyz, N, M, radius2, nsample, idx);
+    ball_query_kernel<true><<<grid, BQ_WARPS * 32, smem, st>>>(new_xyz, xyz, N, M, radius2, nsample, idx); PTT_LAUNCHED();
   } else {
-    ball_query_kernel<false><<<grid, BQ_WARPS * 32, 0, st>>>(new_xyz, xyz, N, M, radius2, nsample, idx);
+    ball_query_kernel<false><<<grid, BQ_WARPS * 32, 0, st>>>(new_xyz, xyz, N, M, radius2, nsample, idx); PTT_LAUNCHED();
   }
   return ptt_launch_status();
 }

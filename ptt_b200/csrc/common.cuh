@@ -17,11 +17,16 @@ static inline int ptt_launch_status() {
   return e == cudaSuccess ? PTT_OK : (int)e;
 }
 
+// Kernel-launch counter behind ptt_launch_count() (bench.py reports it as `gpu_launches`).
+void ptt_count_launches(int n);
+#define PTT_LAUNCHED() ptt_count_launches(1)
+
 static inline cudaStream_t as_stream(ptt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+static inline long long llmin_(long long a, long long b) { return a < b ? a : b; }
 
 // a*a + b*b + c*c exactly as nvcc's default contraction emits it for upstream pointnet2_ops
 // (oracle/probe_contraction.sh): FMUL on the middle term, then two FFMAs.  Written with intrinsics

@@ -78,7 +78,7 @@ extern "C" int ptt_group_points(const float* points, const int* idx, int B, int 
   if (B == 0 || C == 0 || M == 0 || K == 0) return PTT_OK;
   PTT_CHECK_ARG(points && idx && out);
   dim3 grid(ceil_div(M * K, 256), ceil_div(C, 8), B);
-  group_points_kernel<<<grid, 256, 0, as_stream(stream)>>>(points, idx, C, N, M * K, out);
+  group_points_kernel<<<grid, 256, 0, as_stream(stream)>>>(points, idx, C, N, M * K, out); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
@@ -92,7 +92,7 @@ extern "C" int ptt_group_points_grad(const float* grad_out, const int* idx, int 
   if (M == 0 || K == 0) return PTT_OK;
   PTT_CHECK_ARG(grad_out && idx);
   dim3 grid(ceil_div(M * K, 256), ceil_div(C, 8), B);
-  group_points_grad_kernel<<<grid, 256, 0, as_stream(stream)>>>(grad_out, idx, C, N, M * K, grad_points);
+  group_points_grad_kernel<<<grid, 256, 0, as_stream(stream)>>>(grad_out, idx, C, N, M * K, grad_points); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
@@ -101,7 +101,7 @@ extern "C" int ptt_cm_to_pm(const float* src_cm, int B, int C, int N, float* dst
   if (B == 0 || N == 0 || ld == 0) return PTT_OK;
   PTT_CHECK_ARG(dst_pm && (src_cm || C == 0));
   dim3 grid(ceil_div(N, 32), ceil_div(ld, 32), B);
-  cm_to_pm_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src_cm, C, N, dst_pm, ld);
+  cm_to_pm_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src_cm, C, N, dst_pm, ld); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
@@ -110,6 +110,6 @@ extern "C" int ptt_pm_to_cm(const float* src_pm, int ld, int B, int C, int N, fl
   if (B == 0 || N == 0 || C == 0) return PTT_OK;
   PTT_CHECK_ARG(src_pm && dst_cm);
   dim3 grid(ceil_div(N, 32), ceil_div(C, 32), B);
-  pm_to_cm_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src_pm, ld, C, N, dst_cm);
+  pm_to_cm_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src_pm, ld, C, N, dst_cm); PTT_LAUNCHED();
   return ptt_launch_status();
 }

@@ -85,7 +85,7 @@ extern "C" int ptt_three_nn(const float* unknown, const float* known, int B, int
   if (B == 0 || n == 0) return PTT_OK;
   PTT_CHECK_ARG(unknown && dist2 && idx && (known || m == 0));
   dim3 grid(ceil_div(n, 256), B);
-  three_nn_kernel<<<grid, 256, 0, as_stream(stream)>>>(unknown, known, n, m, dist2, idx);
+  three_nn_kernel<<<grid, 256, 0, as_stream(stream)>>>(unknown, known, n, m, dist2, idx); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
@@ -95,7 +95,7 @@ extern "C" int ptt_three_interpolate(const float* points, const int* idx, const 
   if (B == 0 || c == 0 || n == 0) return PTT_OK;
   PTT_CHECK_ARG(points && idx && weight && out);
   dim3 grid(ceil_div(n, 256), c, B);
-  three_interpolate_kernel<<<grid, 256, 0, as_stream(stream)>>>(points, idx, weight, c, m, n, out);
+  three_interpolate_kernel<<<grid, 256, 0, as_stream(stream)>>>(points, idx, weight, c, m, n, out); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
@@ -109,6 +109,6 @@ extern "C" int ptt_three_interpolate_grad(const float* grad_out, const int* idx,
   if (n == 0) return PTT_OK;
   PTT_CHECK_ARG(grad_out && idx && weight);
   dim3 grid(ceil_div(n, 256), c, B);
-  three_interpolate_grad_kernel<<<grid, 256, 0, as_stream(stream)>>>(grad_out, idx, weight, c, n, m, grad_points);
+  three_interpolate_grad_kernel<<<grid, 256, 0, as_stream(stream)>>>(grad_out, idx, weight, c, n, m, grad_points); PTT_LAUNCHED();
   return ptt_launch_status();
 }

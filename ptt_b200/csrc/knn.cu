@@ -62,7 +62,7 @@ template <int NPL>
 int launch_knn(const float* xyz, int B, int n, int k, int* out, cudaStream_t st) {
   const size_t smem = (size_t)3 * n * sizeof(float);
   dim3 grid(min(ceil_div(n, KNN_WARPS), 64), B);
-  knn_kernel<NPL><<<grid, KNN_WARPS * 32, smem, st>>>(xyz, n, k, out);
+  knn_kernel<NPL><<<grid, KNN_WARPS * 32, smem, st>>>(xyz, n, k, out); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 

@@ -1,0 +1,214 @@
+// Set-abstraction layer body for sm_100a, eval mode:
+//   QueryAndGroup (pointnet2_utils.py:320-380) + SharedMLP (pytorch_utils.py:12-36) + max over nsample
+//   (pointnet2_modules.py:83-88), with BatchNorm folded into a per-channel scale/shift.
+//
+// Data layout: activations are POINT-MAJOR (one contiguous row of channels per point / per (centre,
+// sample) pair), so a neighbour gather is a contiguous row copy and every layer is a row-block
+// contraction.  The reference's channel-major (B,C,M,ns) tensors are never built.
+//
+// Stage 1 (this file, v1): rows are materialised once in workspace ([feats | rel_xyz] per pair),
+// the layers run through the row-block contraction of gemm.cuh, a final kernel takes the max over
+// each centre's nsample rows and writes point-major and/or channel-major output.
+#include "gemm.cuh"
+
+namespace {
+
+constexpr int SA_MAX_LAYERS = 4;
+
+struct SaLayout {
+  int n_layers;
+  int dims[SA_MAX_LAYERS + 1];
+  int ldw[SA_MAX_LAYERS];
+  size_t wt[SA_MAX_LAYERS], scale[SA_MAX_LAYERS], shift[SA_MAX_LAYERS];
+  size_t total;
+};
+
+bool sa_layout(int C, int n_layers, const int* h_dims, SaLayout* L) {
+  if (C < 0 || n_layers < 1 || n_layers > SA_MAX_LAYERS || h_dims == nullptr) return false;
+  if (h_dims[0] != C + 3) return false;
+  L->n_layers = n_layers;
+  size_t off = 0;
+  for (int l = 0; l <= n_layers; ++l) {
+    if (h_dims[l] < 1) return false;
+    L->dims[l] = h_dims[l];
+  }
+  for (int l = 0; l < n_layers; ++l) {
+    L->ldw[l] = round_up(L->dims[l + 1], 4);
+    L->wt[l] = off;
+    off += (size_t)L->dims[l] * L->ldw[l];
+    L->scale[l] = off;
+    off += L->ldw[l];
+    L->shift[l] = off;
+    off += L->ldw[l];
+  }
+  L->total = off;
+  return true;
+}
+
+// conv weight (Cout, Cin) with Cin ordered [xyz(3) | feats(C)]  ->  wt (Cin x ldw) with rows ordered
+// [feats(C) | xyz(3)] when permute != 0 (layer 0), else unchanged order.
+__global__ void sa_pack_weight_kernel(const float* __restrict__ w, int Cin, int Cout, int ldw, int C_feat, int permute,
+                                      float* __restrict__ wt) {
+  const int total = Cin * ldw;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int k = e / ldw, c = e - k * ldw;
+    int src_k = k;
+    if (permute) src_k = k < C_feat ? k + 3 : k - C_feat;
+    wt[e] = c < Cout ? w[(size_t)c * Cin + src_k] : 0.f;
+  }
+}
+
+__global__ void sa_pack_vec_kernel(const float* __restrict__ scale, const float* __restrict__ shift, int Cout, int ldw,
+                                   float* __restrict__ dscale, float* __restrict__ dshift) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ldw; c += gridDim.x * blockDim.x) {
+    dscale[c] = c < Cout ? (scale ? scale[c] : 1.f) : 0.f;
+    dshift[c] = c < Cout ? (shift ? shift[c] : 0.f) : 0.f;
+  }
+}
+
+// One warp per (centre, sample) pair: X[row] = [ feats[b, idx, 0:C] | rel_xyz(3) | 0 pad ].
+__global__ void __launch_bounds__(256) sa_group_rows_kernel(const float* __restrict__ xyz, const float* __restrict__ feats,
+                                                             int ldf, const float* __restrict__ new_xyz,
+                                                             const int* __restrict__ idx, int N, int M, int ns, int C,
+                                                             float radius, int normalize, long long rows,
+                                                             float* __restrict__ X, int ldx) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = warp; row < rows; row += nwarps) {
+    const long long cj = row / ns;           // b * M + j
+    const int b = (int)(cj / M);
+    const int i = __ldg(idx + row);
+    const float* src = feats ? feats + ((size_t)b * N + i) * ldf : nullptr;
+    float* dst = X + (size_t)row * ldx;
+    for (int c = lane; c < C; c += 32) dst[c] = __ldg(src + c);
+    if (lane < ldx - C) {
+      float v = 0.f;
+      if (lane < 3) {
+        v = __fsub_rn(__ldg(xyz + ((size_t)b * N + i) * 3 + lane), __ldg(new_xyz + (size_t)cj * 3 + lane));
+        if (normalize) v = __fdiv_rn(v, radius);
+      }
+      dst[C + lane] = v;
+    }
+  }
+}
+
+// out_pm[(b*M+j), c] = max_s H[((b*M+j)*ns + s), c]
+__global__ void __launch_bounds__(256) sa_group_max_kernel(const float* __restrict__ H, int ldh, int ns, int Cout,
+                                                            long long centres, float* __restrict__ out_pm, int ld_out) {
+  const long long total = centres * Cout;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long cj = e / Cout;
+    const int c = (int)(e - cj * Cout);
+    const float* h = H + (size_t)cj * ns * ldh + c;
+    float m = h[0];
+    for (int s = 1; s < ns; ++s) m = fmaxf(m, h[(size_t)s * ldh]);
+    out_pm[(size_t)cj * ld_out + c] = m;
+  }
+}
+
+}  // namespace
+
+extern "C" size_t ptt_sa_params_floats(int C, int n_layers, const int* h_dims) {
+  SaLayout L;
+  return sa_layout(C, n_layers, h_dims, &L) ? L.total : 0;
+}
+
+extern "C" int ptt_sa_pack_params(int C, int n_layers, const int* h_dims, const float* const* h_weights,
+                                  const float* const* h_scale, const float* const* h_shift, float* params,
+                                  ptt_stream_t stream) {
+  SaLayout L;
+  PTT_CHECK_ARG(sa_layout(C, n_layers, h_dims, &L) && h_weights && params);
+  cudaStream_t st = as_stream(stream);
+  for (int l = 0; l < n_layers; ++l) {
+    PTT_CHECK_ARG(h_weights[l] != nullptr);
+    const int total = L.dims[l] * L.ldw[l];
+    sa_pack_weight_kernel<<<min(ceil_div(total, 256), 1024), 256, 0, st>>>(h_weights[l], L.dims[l], L.dims[l + 1],
+                                                                             L.ldw[l], C, l == 0, params + L.wt[l]); PTT_LAUNCHED();
+    sa_pack_vec_kernel<<<ceil_div(L.ldw[l], 256), 256, 0, st>>>(h_scale ? h_scale[l] : nullptr,
+                                                                 h_shift ? h_shift[l] : nullptr, L.dims[l + 1], L.ldw[l],
+                                                                 params + L.scale[l], params + L.shift[l]); PTT_LAUNCHED();
+  }
+  return ptt_launch_status();
+}
+
+namespace {
+struct SaWorkspace {
+  int ldx, ldh;
+  size_t x_off, ha_off, hb_off, pm_off, total;  // in floats
+};
+bool sa_workspace(int B, int M, int ns, int C, const SaLayout& L, SaWorkspace* W) {
+  const size_t rows = (size_t)B * M * ns;
+  int cmax = 0;
+  for (int l = 1; l <= L.n_layers; ++l) cmax = max(cmax, L.dims[l]);
+  W->ldx = round_up(C + 3, 4);
+  W->ldh = round_up(cmax, 4);
+  size_t off = 0;
+  W->x_off = off;  off += align_up(rows * W->ldx, 64);
+  W->ha_off = off; off += align_up(rows * W->ldh, 64);
+  W->hb_off = off; off += align_up(rows * W->ldh, 64);
+  W->pm_off = off; off += align_up((size_t)B * M * W->ldh, 64);
+  W->total = off;
+  return true;
+}
+}  // namespace
+
+extern "C" size_t ptt_sa_mlp_workspace_bytes(int B, int M, int ns, int C, int n_layers, const int* h_dims) {
+  SaLayout L;
+  SaWorkspace W;
+  if (B <= 0 || M <= 0 || ns <= 0 || !sa_layout(C, n_layers, h_dims, &L)) return 0;
+  sa_workspace(B, M, ns, C, L, &W);
+  return W.total * sizeof(float);
+}
+
+extern "C" int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, const float* new_xyz, const int* idx,
+                              int B, int N, int M, int ns, int C, float radius, int normalize_xyz, int n_layers,
+                              const int* h_dims, const float* params, float* out_pm, int ld_out, float* out_cm,
+                              void* workspace, size_t workspace_bytes, ptt_stream_t stream) {
+  SaLayout L;
+  PTT_CHECK_ARG(B >= 0 && N >= 1 && M >= 0 && ns >= 1 && sa_layout(C, n_layers, h_dims, &L));
+  if (B == 0 || M == 0) return PTT_OK;
+  PTT_CHECK_ARG(xyz && new_xyz && idx && params && (out_pm || out_cm));
+  PTT_CHECK_ARG(C == 0 || (feats != nullptr && ldf >= C));
+  const int Cout = L.dims[n_layers];
+  PTT_CHECK_ARG(out_pm == nullptr || ld_out >= Cout);
+  SaWorkspace W;
+  sa_workspace(B, M, ns, C, L, &W);
+  if (workspace == nullptr || workspace_bytes < W.total * sizeof(float)) return PTT_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 15u) != 0) return PTT_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  float* ws = static_cast<float*>(workspace);
+  float* X = ws + W.x_off;
+  float* H[2] = {ws + W.ha_off, ws + W.hb_off};
+  const long long rows = (long long)B * M * ns;
+
+  {
+    const long long blocks = llmin_((rows + 7) / 8, 148LL * 16);
+    sa_group_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(xyz, feats, ldf, new_xyz, idx, N, M, ns, C, radius,
+                                                           normalize_xyz, rows, X, W.ldx); PTT_LAUNCHED();
+  }
+  const float* in = X;
+  int ld_in = W.ldx;
+  for (int l = 0; l < n_layers; ++l) {
+    PttGemmArgs a;
+    a.x = in; a.ldx = ld_in; a.R = (int)rows; a.K = L.dims[l];
+    a.wt = params + L.wt[l]; a.ldw = L.ldw[l]; a.N = L.dims[l + 1];
+    a.scale = params + L.scale[l]; a.shift = params + L.shift[l]; a.relu = 1;
+    a.y = H[l & 1]; a.ldy = W.ldh;
+    int rc = ptt_gemm_launch(a, st);
+    if (rc != PTT_OK) return rc;
+    in = a.y;
+    ld_in = W.ldh;
+  }
+  float* pm = out_pm ? out_pm : ws + W.pm_off;
+  const int ld_pm = out_pm ? ld_out : W.ldh;
+  {
+    const long long total = (long long)B * M * Cout;
+    const long long blocks = llmin_((total + 255) / 256, 148LL * 16);
+    sa_group_max_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, ld_in, ns, Cout, (long long)B * M, pm, ld_pm); PTT_LAUNCHED();
+  }
+  int rc = ptt_launch_status();
+  if (rc != PTT_OK) return rc;
+  if (out_cm) rc = ptt_pm_to_cm(pm, ld_pm, B, Cout, M, out_cm, stream);
+  return rc;
+}

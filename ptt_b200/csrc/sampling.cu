@@ -223,7 +223,7 @@ int launch_fps(const float* xyz, int B, int N, int M, int* idx, float* new_xyz, 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<B, THREADS, smem, st>>>(xyz, N, M, idx, new_xyz);
+  kern<<<B, THREADS, smem, st>>>(xyz, N, M, idx, new_xyz); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
@@ -274,7 +274,7 @@ extern "C" int ptt_furthest_point_sampling(const float* xyz, int B, int N, int n
   }
   const size_t need = ptt_furthest_point_sampling_workspace_bytes(B, N, npoint);
   if (workspace == nullptr || workspace_bytes < need) return PTT_ERR_WORKSPACE;
-  fps_generic_kernel<<<B, 512, 0, st>>>(xyz, nullptr, N, npoint, (float*)workspace, idx, new_xyz);
+  fps_generic_kernel<<<B, 512, 0, st>>>(xyz, nullptr, N, npoint, (float*)workspace, idx, new_xyz); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
@@ -290,7 +290,7 @@ extern "C" int ptt_furthest_point_sampling_with_dist(const float* dist, int B, i
   if (B == 0 || npoint == 0) return PTT_OK;
   PTT_CHECK_ARG(dist != nullptr && idx != nullptr);
   if (workspace == nullptr || workspace_bytes < (size_t)B * N * sizeof(float)) return PTT_ERR_WORKSPACE;
-  fps_generic_kernel<<<B, 512, 0, as_stream(stream)>>>(nullptr, dist, N, npoint, (float*)workspace, idx, nullptr);
+  fps_generic_kernel<<<B, 512, 0, as_stream(stream)>>>(nullptr, dist, N, npoint, (float*)workspace, idx, nullptr); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
@@ -300,7 +300,7 @@ extern "C" int ptt_gather_points(const float* points, const int* idx, int B, int
   if (B == 0 || C == 0 || M == 0) return PTT_OK;
   PTT_CHECK_ARG(points && idx && out);
   dim3 grid(ceil_div(M, 256), ceil_div(C, 8), B);
-  gather_points_kernel<<<grid, 256, 0, as_stream(stream)>>>(points, idx, C, N, M, out);
+  gather_points_kernel<<<grid, 256, 0, as_stream(stream)>>>(points, idx, C, N, M, out); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
@@ -314,6 +314,6 @@ extern "C" int ptt_gather_points_grad(const float* grad_out, const int* idx, int
   if (M == 0) return PTT_OK;
   PTT_CHECK_ARG(grad_out && idx);
   dim3 grid(ceil_div(M, 256), ceil_div(C, 8), B);
-  gather_points_grad_kernel<<<grid, 256, 0, as_stream(stream)>>>(grad_out, idx, C, N, M, grad_points);
+  gather_points_grad_kernel<<<grid, 256, 0, as_stream(stream)>>>(grad_out, idx, C, N, M, grad_points); PTT_LAUNCHED();
   return ptt_launch_status();
 }

@@ -1,0 +1,229 @@
+// Point-Track-Transformer block (kNN vector attention) for sm_100a, forward.
+//   TransformerBlock.forward          transformer_block/variants.py:149-165
+//   TransformerBlockOffset.forward    transformer_block/variants.py:319-334  (variant 1: fc2(x - res))
+//
+//   x = fc1(f); q,k,v = Wq x, Wk x, Wv x                              (rows: B*n tokens)
+//   pos_ij = fc_delta(xyz_i - xyz_j),  j in knn(i)                    (rows: B*n*k pairs)
+//   a_ij   = fc_gamma(q_i - k_j + pos_ij);  p = softmax_j(a / sqrt(d_model))   per channel
+//   res_i  = sum_j p_ij * (v_j + pos_ij);   out = fc2(res) + f
+//
+// Stage 1 (this file, v1): token- and pair-major activations in workspace, the dense contractions
+// through gemm.cuh, the gathers / softmax / weighted sum in fused element kernels.  The (B,n,n)
+// distance matrix, its argsort and the three (B,n,k,d) gathered tensors of the reference are never built.
+#include "gemm.cuh"
+
+namespace {
+
+struct TrLayout {
+  int dp, dm;
+  // linear images (wt rows + bias row), in floats from the start of the params block
+  size_t fc1, qkv, delta0, delta2, gamma0, gamma2, fc2, total;
+};
+
+bool tr_layout(int dp, int dm, TrLayout* L) {
+  if (dp < 1 || dm < 1) return false;
+  L->dp = dp; L->dm = dm;
+  size_t off = 0;
+  auto take = [&](int K, int Cout) { size_t o = off; off += align_up((size_t)(K + 1) * round_up(Cout, 4), 4); return o; };
+  L->fc1 = take(dp, dm);
+  L->qkv = take(dm, 3 * round_up(dm, 4));
+  L->delta0 = take(3, dm);
+  L->delta2 = take(dm, dm);
+  L->gamma0 = take(dm, dm);
+  L->gamma2 = take(dm, dm);
+  L->fc2 = take(dm, dp);
+  L->total = off;
+  return true;
+}
+
+// h[(b,i,j), c] = relu(Wd0[c,:] . (xyz_i - xyz_knn(i,j)) + bd0[c])      delta0 image: 3 rows wt + bias row
+__global__ void __launch_bounds__(256) tr_delta0_kernel(const float* __restrict__ xyz, const int* __restrict__ knn,
+                                                         const float* __restrict__ img, int n, int k, int dm, int ldw,
+                                                         long long pairs, float* __restrict__ h, int ldh) {
+  const long long total = pairs * dm;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long pr = e / dm;
+    const int c = (int)(e - pr * dm);
+    const long long tok = pr / k;            // b * n + i
+    const long long b = tok / n;
+    const int j = __ldg(knn + pr);
+    const float* pi = xyz + tok * 3;
+    const float* pj = xyz + (b * n + j) * 3;
+    const float dx = __ldg(pi) - __ldg(pj), dy = __ldg(pi + 1) - __ldg(pj + 1), dz = __ldg(pi + 2) - __ldg(pj + 2);
+    float v = __ldg(img + 3 * ldw + c);
+    v = fmaf(dx, __ldg(img + c), v);
+    v = fmaf(dy, __ldg(img + ldw + c), v);
+    v = fmaf(dz, __ldg(img + 2 * ldw + c), v);
+    h[(size_t)pr * ldh + c] = fmaxf(v, 0.f);
+  }
+}
+
+// a[(b,i,j), c] = q[(b,i), c] - kk[(b,knn), c] + pos[(b,i,j), c]
+__global__ void __launch_bounds__(256) tr_attn_in_kernel(const float* __restrict__ qkv, int ldq, int koff,
+                                                          const int* __restrict__ knn, const float* __restrict__ pos,
+                                                          int n, int k, int dm, long long pairs, float* __restrict__ a,
+                                                          int ld) {
+  const long long total = pairs * dm;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long pr = e / dm;
+    const int c = (int)(e - pr * dm);
+    const long long tok = pr / k;
+    const long long b = tok / n;
+    const int j = __ldg(knn + pr);
+    const float q = __ldg(qkv + tok * ldq + c);
+    const float kk = __ldg(qkv + (b * n + j) * ldq + koff + c);
+    a[(size_t)pr * ld + c] = (q - kk) + __ldg(pos + (size_t)pr * ld + c);
+  }
+}
+
+// per (token, channel): p = softmax_j(logit / sqrt(dm)); res = sum_j p * (v[knn] + pos)
+__global__ void __launch_bounds__(256) tr_softmax_agg_kernel(const float* __restrict__ logit, const float* __restrict__ pos,
+                                                              int ld, const float* __restrict__ qkv, int ldq, int voff,
+                                                              const int* __restrict__ knn, int n, int k, int dm,
+                                                              float divisor, long long tokens, const float* __restrict__ x_sub,
+                                                              float* __restrict__ res, int ldres, float* __restrict__ attn) {
+  const long long total = tokens * dm;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long tok = e / dm;
+    const int c = (int)(e - tok * dm);
+    const long long b = tok / n;
+    const float* lg = logit + (size_t)tok * k * ld + c;
+    float m = -INFINITY;
+    for (int j = 0; j < k; ++j) m = fmaxf(m, lg[(size_t)j * ld] / divisor);
+    float s = 0.f;
+    for (int j = 0; j < k; ++j) s += expf(lg[(size_t)j * ld] / divisor - m);
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const float p = expf(lg[(size_t)j * ld] / divisor - m) / s;
+      const int nb = __ldg(knn + tok * k + j);
+      const float v = __ldg(qkv + (b * n + nb) * ldq + voff + c);
+      acc = fmaf(p, v + __ldg(pos + ((size_t)tok * k + j) * ld + c), acc);
+      if (attn) attn[((size_t)tok * k + j) * dm + c] = p;
+    }
+    if (x_sub) acc = __ldg(x_sub + tok * (long long)ldres + c) - acc;  // Offset variant: fc2(x - res)
+    res[(size_t)tok * ldres + c] = acc;
+  }
+}
+
+struct TrWorkspace {
+  int ld;      // row stride of dm-wide activations
+  int ldq;     // row stride of the qkv block (3 * ld)
+  size_t knn, x, qkv, h, pos, a, res, total;  // float offsets
+};
+
+void tr_workspace(int B, int n, int k, const TrLayout& L, TrWorkspace* W) {
+  const size_t tokens = (size_t)B * n, pairs = tokens * k;
+  W->ld = round_up(L.dm, 4);
+  W->ldq = 3 * W->ld;
+  size_t off = 0;
+  auto take = [&](size_t cnt) { size_t o = off; off += align_up(cnt, 64); return o; };
+  W->knn = take(pairs);
+  W->x = take(tokens * W->ld);
+  W->qkv = take(tokens * W->ldq);
+  W->res = take(tokens * W->ld);
+  W->h = take(pairs * W->ld);
+  W->pos = take(pairs * W->ld);
+  W->a = take(pairs * W->ld);
+  W->total = off;
+}
+
+inline unsigned grid_for(long long total) { return (unsigned)llmin_((total + 255) / 256, 148LL * 32); }
+
+}  // namespace
+
+extern "C" size_t ptt_transformer_params_floats(int d_points, int d_model) {
+  TrLayout L;
+  return tr_layout(d_points, d_model, &L) ? L.total : 0;
+}
+
+extern "C" int ptt_transformer_pack_params(int d_points, int d_model, const float* fc1_w, const float* fc1_b,
+                                           const float* fc2_w, const float* fc2_b, const float* delta0_w,
+                                           const float* delta0_b, const float* delta2_w, const float* delta2_b,
+                                           const float* gamma0_w, const float* gamma0_b, const float* gamma2_w,
+                                           const float* gamma2_b, const float* wq, const float* wk, const float* wv,
+                                           float* params, ptt_stream_t stream) {
+  TrLayout L;
+  PTT_CHECK_ARG(tr_layout(d_points, d_model, &L) && params);
+  PTT_CHECK_ARG(fc1_w && fc2_w && delta0_w && delta2_w && gamma0_w && gamma2_w && wq && wk && wv);
+  cudaStream_t st = as_stream(stream);
+  const int dp = d_points, dm = d_model, ld = round_up(dm, 4);
+  cudaError_t e = cudaMemsetAsync(params, 0, L.total * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  int rc;
+  if ((rc = ptt_linear_pack_cols(fc1_w, fc1_b, dp, dm, ld, 0, params + L.fc1, st))) return rc;
+  if ((rc = ptt_linear_pack_cols(wq, nullptr, dm, dm, 3 * ld, 0, params + L.qkv, st))) return rc;
+  if ((rc = ptt_linear_pack_cols(wk, nullptr, dm, dm, 3 * ld, ld, params + L.qkv, st))) return rc;
+  if ((rc = ptt_linear_pack_cols(wv, nullptr, dm, dm, 3 * ld, 2 * ld, params + L.qkv, st))) return rc;
+  if ((rc = ptt_linear_pack_cols(delta0_w, delta0_b, 3, dm, ld, 0, params + L.delta0, st))) return rc;
+  if ((rc = ptt_linear_pack_cols(delta2_w, delta2_b, dm, dm, ld, 0, params + L.delta2, st))) return rc;
+  if ((rc = ptt_linear_pack_cols(gamma0_w, gamma0_b, dm, dm, ld, 0, params + L.gamma0, st))) return rc;
+  if ((rc = ptt_linear_pack_cols(gamma2_w, gamma2_b, dm, dm, ld, 0, params + L.gamma2, st))) return rc;
+  if ((rc = ptt_linear_pack_cols(fc2_w, fc2_b, dm, dp, round_up(dp, 4), 0, params + L.fc2, st))) return rc;
+  return PTT_OK;
+}
+
+extern "C" size_t ptt_transformer_block_workspace_bytes(int B, int n, int k, int d_points, int d_model) {
+  TrLayout L;
+  TrWorkspace W;
+  if (B <= 0 || n <= 0 || k <= 0 || !tr_layout(d_points, d_model, &L)) return 0;
+  tr_workspace(B, n, k, L, &W);
+  return W.total * sizeof(float);
+}
+
+extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features, int B, int n, int k, int d_points,
+                                         int d_model, int variant, const float* params, const int* knn_idx_or_null,
+                                         float* out, float* attn_or_null, void* workspace, size_t workspace_bytes,
+                                         ptt_stream_t stream) {
+  TrLayout L;
+  PTT_CHECK_ARG(B >= 0 && n >= 1 && k >= 1 && k <= n && tr_layout(d_points, d_model, &L));
+  PTT_CHECK_ARG(variant == 0 || variant == 1);
+  if (B == 0) return PTT_OK;
+  PTT_CHECK_ARG(xyz && features && params && out);
+  TrWorkspace W;
+  tr_workspace(B, n, k, L, &W);
+  if (workspace == nullptr || workspace_bytes < W.total * sizeof(float)) return PTT_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 15u) != 0) return PTT_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  float* ws = static_cast<float*>(workspace);
+  const int dp = d_points, dm = d_model, ld = W.ld, ldq = W.ldq;
+  const long long tokens = (long long)B * n, pairs = tokens * k;
+  int rc;
+
+  const int* knn = knn_idx_or_null;
+  if (knn == nullptr) {
+    int* own = reinterpret_cast<int*>(ws + W.knn);
+    if ((rc = ptt_knn(xyz, B, n, k, own, stream))) return rc;
+    knn = own;
+  }
+  float* x = ws + W.x;
+  float* qkv = ws + W.qkv;
+  float* h = ws + W.h;
+  float* pos = ws + W.pos;
+  float* a = ws + W.a;
+  float* res = ws + W.res;
+
+  auto linear = [&](const float* in, int ldin, long long R, int K, size_t img, int Cout, int ldw, bool bias, int relu,
+                    const float* residual, int ldr, float* y, int ldy) {
+    PttGemmArgs g;
+    g.x = in; g.ldx = ldin; g.R = (int)R; g.K = K;
+    g.wt = params + img; g.ldw = ldw; g.N = Cout;
+    g.shift = bias ? params + img + (size_t)K * ldw : nullptr;
+    g.relu = relu;
+    g.residual = residual; g.ldr = ldr;
+    g.y = y; g.ldy = ldy;
+    return ptt_gemm_launch(g, st);
+  };
+
+  if ((rc = linear(features, dp, tokens, dp, L.fc1, dm, ld, true, 0, nullptr, 0, x, ld))) return rc;
+  if ((rc = linear(x, ld, tokens, dm, L.qkv, 3 * ld, 3 * ld, false, 0, nullptr, 0, qkv, ldq))) return rc;
+  tr_delta0_kernel<<<grid_for(pairs * dm), 256, 0, st>>>(xyz, knn, params + L.delta0, n, k, dm, ld, pairs, h, ld); PTT_LAUNCHED();
+  if ((rc = linear(h, ld, pairs, dm, L.delta2, dm, ld, true, 0, nullptr, 0, pos, ld))) return rc;
+  tr_attn_in_kernel<<<grid_for(pairs * dm), 256, 0, st>>>(qkv, ldq, ld, knn, pos, n, k, dm, pairs, a, ld); PTT_LAUNCHED();
+  if ((rc = linear(a, ld, pairs, dm, L.gamma0, dm, ld, true, 1, nullptr, 0, h, ld))) return rc;
+  if ((rc = linear(h, ld, pairs, dm, L.gamma2, dm, ld, true, 0, nullptr, 0, a, ld))) return rc;
+  tr_softmax_agg_kernel<<<grid_for(tokens * dm), 256, 0, st>>>(a, pos, ld, qkv, ldq, 2 * ld, knn, n, k, dm,
+                                                                sqrtf((float)dm), tokens, variant == 1 ? x : nullptr, res,
+                                                                ld, attn_or_null); PTT_LAUNCHED();
+  if ((rc = ptt_launch_status())) return rc;
+  return linear(res, ld, tokens, dm, L.fc2, dp, round_up(dp, 4), true, 0, features, dp, out, dp);
+}

@@ -1,0 +1,186 @@
+"""The PTT per-frame point-feature hot path on one B200, driven entirely through the C ABI.
+
+`HotPath` is the product twin of oracle.torch_port.hot_path_frame (the checker): the functions
+a1-a9 of SURVEY.md section 8 in dependency order --
+
+    search / template clouds -> backbone SA1-3 (x2 branches) + cov_final   pointnet2_backbone.py:41-67
+    centroid-head transformer block on (search_seeds, search_feats^T)       centroids_voting_head.py:71-76
+    box-head SA on (votes = search_seeds, votes_feats = [score | feats])    box_voting_head.py:75-79
+    box-head transformer block                                              box_voting_head.py:81-86
+
+-- with the non-hot modules between them (CosineSimAug, the heads' Conv1d stacks; SURVEY.md 8(f)
+N1/N2) replaced by the same fixed glue the checker uses, so that real tensors flow from one hot
+stage into the next.  Parameters come from a state_dict with the reference's own key names, so a
+reference checkpoint drives it unchanged.  Eval mode (BatchNorm folded).
+"""
+import torch
+
+from . import ops
+
+DEFAULT_CFG = dict(npoints_search=(512, 256, 128), npoints_template=(256, 128, 64), radii=(0.3, 0.5, 0.7),
+                   nsamples=(32, 32, 32), sample_methods=("fps", "sequence", "sequence"), normalize_xyz=True,
+                   knn=16, box_npoint=64, box_radius=0.3, box_nsample=16, bn_eps=1e-5)
+
+
+def _sub(sd, prefix):
+    n = len(prefix)
+    return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def pack_sa_module(sd, eps=1e-5):
+    """state_dict of one PointnetSAModuleVotes (keys mlp_module.layer{i}.conv.weight, ...normlayer.bn.*)."""
+    ws, scales, shifts = [], [], []
+    i = 0
+    while "mlp_module.layer%d.conv.weight" % i in sd:
+        p = "mlp_module.layer%d." % i
+        w = sd[p + "conv.weight"]
+        ws.append(w.reshape(w.shape[0], w.shape[1]))
+        if p + "normlayer.bn.weight" in sd:
+            s, t = ops.fold_batchnorm(sd[p + "normlayer.bn.weight"], sd[p + "normlayer.bn.bias"],
+                                      sd[p + "normlayer.bn.running_mean"], sd[p + "normlayer.bn.running_var"], eps)
+            if p + "conv.bias" in sd:
+                t = t + sd[p + "conv.bias"] * s
+        else:
+            s, t = None, sd.get(p + "conv.bias")
+        scales.append(s)
+        shifts.append(t)
+        i += 1
+    return ops.PackedSAMlp(ws, scales, shifts)
+
+
+class HotPath:
+    def __init__(self, state_dict, cfg=None, device="cuda"):
+        self.cfg = dict(DEFAULT_CFG)
+        self.cfg.update(cfg or {})
+        self.device = torch.device(device)
+        sd = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state_dict.items()
+              if v.is_floating_point()}
+        eps = self.cfg["bn_eps"]
+        bb = _sub(sd, "backbone_3d.")
+        self.sa = [pack_sa_module(_sub(bb, "SA_modules.%d." % l), eps) for l in range(3)]
+        cw = bb["cov_final.weight"]
+        self.cov_final = ops.PackedLinear(cw.reshape(cw.shape[0], cw.shape[1]).contiguous(), bb["cov_final.bias"])
+        self.centroid_tr = ops.PackedTransformer(_sub(sd, "centroid_voting_head.transformer_block."), self.cfg["knn"])
+        self.box_sa = pack_sa_module(_sub(sd, "box_voting_head.vote_aggregation."), eps)
+        self.box_tr = ops.PackedTransformer(_sub(sd, "box_voting_head.transformer_block."), self.cfg["knn"])
+        self.streams = None
+        self.stage_events = None      # set to {} to record (start, end) CUDA events per stage on its stream
+
+    def profile(self, on=True):
+        self.stage_events = {} if on else None
+
+    def stage_ms(self):
+        """Mean milliseconds per stage over the recorded steps (call after a synchronize)."""
+        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in (self.stage_events or {}).items()}
+
+    class _Stage:
+        def __init__(self, hp, name):
+            self.hp, self.name = hp, name
+
+        def __enter__(self):
+            if self.hp.stage_events is not None:
+                self.start = torch.cuda.Event(enable_timing=True)
+                self.start.record()
+
+        def __exit__(self, *a):
+            if self.hp.stage_events is not None:
+                end = torch.cuda.Event(enable_timing=True)
+                end.record()
+                self.hp.stage_events.setdefault(self.name, []).append((self.start, end))
+            return False
+
+    # a6: one set-abstraction layer (pointnet2_modules.py:57-90), point-major in / out
+    def _sa_layer(self, packed, xyz, feats_pm, npoint, radius, nsample, method, want_cm=False, tag="sa"):
+        c = self.cfg
+        if method == "fps":
+            with self._Stage(self, tag + ".fps"):
+                inds, new_xyz = ops.furthest_point_sampling(xyz, npoint, return_new_xyz=True)
+        elif method in ("sequence", "rs"):
+            inds = None                                    # arange(npoint): the centres are a prefix
+            new_xyz = xyz[:, :npoint].contiguous()
+        else:
+            raise NotImplementedError(method)
+        with self._Stage(self, tag + ".ball_query"):
+            idx = ops.ball_query(new_xyz, xyz, radius, nsample)
+        with self._Stage(self, tag + ".mlp"):
+            out_pm, out_cm = ops.sa_mlp_fwd(packed, xyz, feats_pm, new_xyz, idx, radius, c["normalize_xyz"],
+                                            want_pm=True, want_cm=want_cm)
+        return new_xyz, out_pm, out_cm, inds
+
+    # a8: PointNet2BackboneLight.branch_forward (pointnet2_backbone.py:41-50)
+    def backbone_branch(self, pts, npoints, tag="search"):
+        c = self.cfg
+        xyz, feats = pts, None
+        inds = []
+        for l in range(3):
+            xyz, feats, _, i = self._sa_layer(self.sa[l], xyz, feats, npoints[l], c["radii"][l], c["nsamples"][l],
+                                              c["sample_methods"][l], tag="%s.sa%d" % (tag, l + 1))
+            inds.append(i)
+        B, n3, cdim = feats.shape
+        feat_pm = self.cov_final(feats.reshape(B * n3, cdim)).reshape(B, n3, -1)        # :46 (1x1 Conv1d == row linear)
+        composed = None
+        for i in inds:                                                                  # :48
+            cur = i.long() if i is not None else None
+            if composed is None:
+                composed = cur
+            elif cur is not None:
+                composed = composed.gather(1, cur)
+            else:
+                composed = composed            # arange prefix: narrowing happens below
+        if composed is None:
+            composed = torch.arange(n3, device=pts.device).repeat(B, 1)
+        composed = composed[:, :n3].contiguous()
+        return xyz, feat_pm, composed
+
+    def forward(self, search, template):
+        """search (B,Ns,3), template (B,Nt,3) CUDA fp32 -> dict (same keys / layouts as the checker)."""
+        c = self.cfg
+        if self.streams is None:
+            self.streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        cur = torch.cuda.current_stream()
+        s1, s2 = self.streams
+        s1.wait_stream(cur)
+        s2.wait_stream(cur)
+        with torch.cuda.stream(s2):      # template branch overlaps the search branch (independent clouds)
+            t_xyz, t_feat_pm, t_inds = self.backbone_branch(template, c["npoints_template"], "template")
+            t_feat = ops.pm_to_cm(t_feat_pm)
+        with torch.cuda.stream(s1):
+            s_xyz, s_feat_pm, s_inds = self.backbone_branch(search, c["npoints_search"])
+            s_feat = ops.pm_to_cm(s_feat_pm)
+            with self._Stage(self, "centroid.transformer"):
+                cen = ops.transformer_block_fwd(self.centroid_tr, s_xyz, s_feat_pm)
+            votes_pm = torch.cat([torch.full_like(cen[:, :, :1], 0.5), cen], dim=2)     # glue: [score | feats]
+            b_xyz, b_feat_pm, b_feat, _ = self._sa_layer(self.box_sa, s_xyz, votes_pm, c["box_npoint"], c["box_radius"],
+                                                         c["box_nsample"], "fps", want_cm=True, tag="box.sa")
+            with self._Stage(self, "box.transformer"):
+                box = ops.transformer_block_fwd(self.box_tr, b_xyz, b_feat_pm)
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+        for t in (t_xyz, t_feat_pm, t_feat, t_inds, s_xyz, s_feat_pm, s_feat, s_inds, cen, votes_pm, b_xyz, b_feat_pm,
+                  b_feat, box):
+            t.record_stream(cur)
+        return {"search_seeds": s_xyz, "search_feats": s_feat, "search_inds": s_inds,
+                "template_seeds": t_xyz, "template_feats": t_feat, "template_inds": t_inds,
+                "centroid_feats": cen, "box_centers": b_xyz, "box_sa_feats": b_feat, "box_feats": box}
+
+    __call__ = forward
+
+    HOST_KEYS = ("search_seeds", "search_feats", "search_inds", "template_seeds", "template_feats", "template_inds",
+                 "centroid_feats", "box_centers", "box_sa_feats", "box_feats")
+
+    def forward_host(self, search_host, template_host):
+        """The call a host-side user makes: CPU tensors in (pinned memory makes the copies asynchronous), CPU
+        tensors out (persistent pinned buffers, overwritten by the next call).  Host->device copies of the clouds
+        and device->host copies of every output are part of the call; returns after the results have landed."""
+        dev = self.device
+        search = search_host.to(dev, non_blocking=True)
+        template = template_host.to(dev, non_blocking=True)
+        out = self.forward(search, template)
+        bufs = getattr(self, "_host_out", None)
+        if bufs is None or any(tuple(bufs[k].shape) != tuple(out[k].shape) for k in self.HOST_KEYS):
+            bufs = {k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True) for k in self.HOST_KEYS}
+            self._host_out = bufs
+        for k in self.HOST_KEYS:
+            bufs[k].copy_(out[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return bufs

@@ -1,0 +1,371 @@
+"""Tensor-level wrappers of the C ABI (include/ptt_b200.h): argument checks, output allocation, stream.
+
+PyTorch is used for device memory and the current CUDA stream only.  Every function enqueues on
+`torch.cuda.current_stream()` and never synchronises.  Inputs must be contiguous CUDA tensors of the
+stated dtype (RuntimeError otherwise, like the reference's `_ext`); outputs are fresh tensors.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import PttError, check
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _req(t, dtype, ndim, name):
+    if not isinstance(t, torch.Tensor):
+        raise PttError("%s must be a tensor" % name)
+    if not t.is_cuda:
+        raise PttError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != dtype:
+        raise PttError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if t.dim() != ndim:
+        raise PttError("%s must have %d dimensions, got shape %s" % (name, ndim, tuple(t.shape)))
+    if not t.is_contiguous():
+        raise PttError("%s must be contiguous" % name)
+    return t
+
+
+def _same_device(*ts):
+    dev = ts[0].device
+    for t in ts[1:]:
+        if t is not None and t.device != dev:
+            raise PttError("tensors live on different devices")
+    return dev
+
+
+class _DeviceGuard:
+    def __init__(self, dev):
+        self.g = torch.cuda.device(dev)
+
+    def __enter__(self):
+        self.g.__enter__()
+
+    def __exit__(self, *a):
+        return self.g.__exit__(*a)
+
+
+_F, _I = torch.float32, torch.int32
+
+
+def _workspace(nbytes, dev):
+    return torch.empty(max(int(nbytes), 16) // 4 + 4, dtype=_F, device=dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# the pointnet2_ops `_ext` surface (pointnet2_utils.py:48-287)
+# ------------------------------------------------------------------------------------------------
+def furthest_point_sampling(xyz, npoint, return_new_xyz=False):
+    _req(xyz, _F, 3, "xyz")
+    B, N, three = xyz.shape
+    npoint = int(npoint)
+    if three != 3 or N < 1 or npoint < 0:
+        raise PttError("furthest_point_sampling: xyz must be (B,N>=1,3) and npoint >= 0")
+    with _DeviceGuard(xyz.device):
+        idx = torch.empty(B, npoint, dtype=_I, device=xyz.device)
+        new_xyz = torch.empty(B, npoint, 3, dtype=_F, device=xyz.device) if return_new_xyz else None
+        L = _lib.lib()
+        ws_bytes = L.ptt_furthest_point_sampling_workspace_bytes(B, N, npoint)
+        ws = _workspace(ws_bytes, xyz.device) if ws_bytes else None
+        check(L.ptt_furthest_point_sampling(_ptr(xyz), B, N, npoint, _ptr(idx), _ptr(new_xyz), _ptr(ws), ws_bytes,
+                                            _stream()), "ptt_furthest_point_sampling")
+    return (idx, new_xyz) if return_new_xyz else idx
+
+
+def furthest_point_sampling_with_dist(dist, npoint):
+    _req(dist, _F, 3, "dist")
+    B, N, N2 = dist.shape
+    npoint = int(npoint)
+    if N != N2 or N < 1 or npoint < 0:
+        raise PttError("furthest_point_sampling_with_dist: dist must be (B,N,N)")
+    with _DeviceGuard(dist.device):
+        idx = torch.empty(B, npoint, dtype=_I, device=dist.device)
+        L = _lib.lib()
+        ws_bytes = L.ptt_furthest_point_sampling_with_dist_workspace_bytes(B, N, npoint)
+        ws = _workspace(ws_bytes, dist.device)
+        check(L.ptt_furthest_point_sampling_with_dist(_ptr(dist), B, N, npoint, _ptr(idx), _ptr(ws), ws_bytes, _stream()),
+              "ptt_furthest_point_sampling_with_dist")
+    return idx
+
+
+def gather_points(points, idx):
+    _req(points, _F, 3, "points"), _req(idx, _I, 2, "idx")
+    dev = _same_device(points, idx)
+    B, C, N = points.shape
+    M = idx.shape[1]
+    if idx.shape[0] != B:
+        raise PttError("gather_points: batch mismatch")
+    with _DeviceGuard(dev):
+        out = torch.empty(B, C, M, dtype=_F, device=dev)
+        check(_lib.lib().ptt_gather_points(_ptr(points), _ptr(idx), B, C, N, M, _ptr(out), _stream()), "ptt_gather_points")
+    return out
+
+
+def gather_points_grad(grad_out, idx, n):
+    _req(grad_out, _F, 3, "grad_out"), _req(idx, _I, 2, "idx")
+    dev = _same_device(grad_out, idx)
+    B, C, M = grad_out.shape
+    if tuple(idx.shape) != (B, M):
+        raise PttError("gather_points_grad: idx must be (B,M)")
+    with _DeviceGuard(dev):
+        out = torch.empty(B, C, int(n), dtype=_F, device=dev)
+        check(_lib.lib().ptt_gather_points_grad(_ptr(grad_out), _ptr(idx), B, C, int(n), M, _ptr(out), _stream()),
+              "ptt_gather_points_grad")
+    return out
+
+
+def ball_query(new_xyz, xyz, radius, nsample):
+    _req(new_xyz, _F, 3, "new_xyz"), _req(xyz, _F, 3, "xyz")
+    dev = _same_device(new_xyz, xyz)
+    B, M, _ = new_xyz.shape
+    N = xyz.shape[1]
+    if xyz.shape[0] != B or xyz.shape[2] != 3 or new_xyz.shape[2] != 3 or N < 1:
+        raise PttError("ball_query: new_xyz (B,M,3), xyz (B,N,3)")
+    with _DeviceGuard(dev):
+        idx = torch.empty(B, M, int(nsample), dtype=_I, device=dev)
+        check(_lib.lib().ptt_ball_query(_ptr(new_xyz), _ptr(xyz), B, N, M, float(radius), int(nsample), _ptr(idx), _stream()),
+              "ptt_ball_query")
+    return idx
+
+
+def group_points(points, idx):
+    _req(points, _F, 3, "points"), _req(idx, _I, 3, "idx")
+    dev = _same_device(points, idx)
+    B, C, N = points.shape
+    _, M, K = idx.shape
+    if idx.shape[0] != B:
+        raise PttError("group_points: batch mismatch")
+    with _DeviceGuard(dev):
+        out = torch.empty(B, C, M, K, dtype=_F, device=dev)
+        check(_lib.lib().ptt_group_points(_ptr(points), _ptr(idx), B, C, N, M, K, _ptr(out), _stream()), "ptt_group_points")
+    return out
+
+
+def group_points_grad(grad_out, idx, n):
+    _req(grad_out, _F, 4, "grad_out"), _req(idx, _I, 3, "idx")
+    dev = _same_device(grad_out, idx)
+    B, C, M, K = grad_out.shape
+    if tuple(idx.shape) != (B, M, K):
+        raise PttError("group_points_grad: idx must be (B,M,K)")
+    with _DeviceGuard(dev):
+        out = torch.empty(B, C, int(n), dtype=_F, device=dev)
+        check(_lib.lib().ptt_group_points_grad(_ptr(grad_out), _ptr(idx), B, C, int(n), M, K, _ptr(out), _stream()),
+              "ptt_group_points_grad")
+    return out
+
+
+def three_nn(unknown, known):
+    _req(unknown, _F, 3, "unknown"), _req(known, _F, 3, "known")
+    dev = _same_device(unknown, known)
+    B, n, _ = unknown.shape
+    m = known.shape[1]
+    with _DeviceGuard(dev):
+        dist2 = torch.empty(B, n, 3, dtype=_F, device=dev)
+        idx = torch.empty(B, n, 3, dtype=_I, device=dev)
+        check(_lib.lib().ptt_three_nn(_ptr(unknown), _ptr(known), B, n, m, _ptr(dist2), _ptr(idx), _stream()), "ptt_three_nn")
+    return dist2, idx
+
+
+def three_interpolate(points, idx, weight):
+    _req(points, _F, 3, "points"), _req(idx, _I, 3, "idx"), _req(weight, _F, 3, "weight")
+    dev = _same_device(points, idx, weight)
+    B, c, m = points.shape
+    n = idx.shape[1]
+    with _DeviceGuard(dev):
+        out = torch.empty(B, c, n, dtype=_F, device=dev)
+        check(_lib.lib().ptt_three_interpolate(_ptr(points), _ptr(idx), _ptr(weight), B, c, m, n, _ptr(out), _stream()),
+              "ptt_three_interpolate")
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    _req(grad_out, _F, 3, "grad_out"), _req(idx, _I, 3, "idx"), _req(weight, _F, 3, "weight")
+    dev = _same_device(grad_out, idx, weight)
+    B, c, n = grad_out.shape
+    with _DeviceGuard(dev):
+        out = torch.empty(B, c, int(m), dtype=_F, device=dev)
+        check(_lib.lib().ptt_three_interpolate_grad(_ptr(grad_out), _ptr(idx), _ptr(weight), B, c, n, int(m), _ptr(out),
+                                                    _stream()), "ptt_three_interpolate_grad")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# layout helpers, kNN, linear
+# ------------------------------------------------------------------------------------------------
+def cm_to_pm(src, ld=None):
+    """(B,C,N) -> (B,N,ld) point-major, zero padded."""
+    _req(src, _F, 3, "src")
+    B, C, N = src.shape
+    ld = C if ld is None else int(ld)
+    with _DeviceGuard(src.device):
+        dst = torch.empty(B, N, ld, dtype=_F, device=src.device)
+        check(_lib.lib().ptt_cm_to_pm(_ptr(src), B, C, N, _ptr(dst), ld, _stream()), "ptt_cm_to_pm")
+    return dst
+
+
+def pm_to_cm(src, C=None):
+    """(B,N,ld)[:, :, :C] -> (B,C,N) channel-major."""
+    _req(src, _F, 3, "src")
+    B, N, ld = src.shape
+    C = ld if C is None else int(C)
+    with _DeviceGuard(src.device):
+        dst = torch.empty(B, C, N, dtype=_F, device=src.device)
+        check(_lib.lib().ptt_pm_to_cm(_ptr(src), ld, B, C, N, _ptr(dst), _stream()), "ptt_pm_to_cm")
+    return dst
+
+
+def knn(xyz, k):
+    _req(xyz, _F, 3, "xyz")
+    B, n, _ = xyz.shape
+    with _DeviceGuard(xyz.device):
+        out = torch.empty(B, n, int(k), dtype=_I, device=xyz.device)
+        check(_lib.lib().ptt_knn(_ptr(xyz), B, n, int(k), _ptr(out), _stream()), "ptt_knn")
+    return out
+
+
+class PackedLinear:
+    """nn.Linear parameters in the library's packed layout (ptt_linear_pack)."""
+
+    def __init__(self, weight, bias=None):
+        _req(weight, _F, 2, "weight")
+        self.cout, self.k = weight.shape
+        L = _lib.lib()
+        with _DeviceGuard(weight.device):
+            self.params = torch.empty(L.ptt_linear_params_floats(self.k, self.cout), dtype=_F, device=weight.device)
+            check(L.ptt_linear_pack(_ptr(weight), _ptr(bias), self.k, self.cout, _ptr(self.params), _stream()),
+                  "ptt_linear_pack")
+
+    def __call__(self, x, relu=False, residual=None):
+        _req(x, _F, 2, "x")
+        R, K = x.shape
+        if K != self.k:
+            raise PttError("linear: x has %d columns, weight expects %d" % (K, self.k))
+        with _DeviceGuard(x.device):
+            y = torch.empty(R, self.cout, dtype=_F, device=x.device)
+            check(_lib.lib().ptt_linear_fwd(_ptr(x), K, R, K, _ptr(self.params), self.cout, int(relu), _ptr(residual),
+                                            self.cout if residual is not None else 0, _ptr(y), self.cout, _stream()),
+                  "ptt_linear_fwd")
+        return y
+
+
+# ------------------------------------------------------------------------------------------------
+# fused SA layer body and transformer block
+# ------------------------------------------------------------------------------------------------
+def fold_batchnorm(weight, bias, running_mean, running_var, eps=1e-5):
+    """BatchNorm2d (eval) -> per-channel (scale, shift):  y = scale * x + shift."""
+    scale = weight / torch.sqrt(running_var + eps)
+    return scale.contiguous(), (bias - running_mean * scale).contiguous()
+
+
+class PackedSAMlp:
+    """SharedMLP of one SA layer (pytorch_utils.py:12-36) packed for ptt_sa_mlp_fwd.
+
+    weights[l]: conv weight (Cout_l, Cin_l) with layer-0 input channels in the reference order
+    [xyz(3) | feats(C)]; scales/shifts: folded BatchNorm (or None)."""
+
+    def __init__(self, weights, scales, shifts):
+        self.n_layers = len(weights)
+        ws = [_req(w.reshape(w.shape[0], w.shape[1]).contiguous(), _F, 2, "weight") for w in weights]
+        dims = [ws[0].shape[1]] + [w.shape[0] for w in ws]
+        self.C = dims[0] - 3
+        self.dims = dims
+        self.h_dims = (ctypes.c_int * len(dims))(*dims)
+        dev = ws[0].device
+        L = _lib.lib()
+        n = L.ptt_sa_params_floats(self.C, self.n_layers, self.h_dims)
+        if n == 0:
+            raise PttError("ptt_sa_params_floats rejected dims %s" % (dims,))
+
+        def arr(ts):
+            return (ctypes.c_void_p * self.n_layers)(*[t.data_ptr() if t is not None else None for t in ts])
+
+        scales = [s.contiguous() if s is not None else None for s in (scales or [None] * self.n_layers)]
+        shifts = [s.contiguous() if s is not None else None for s in (shifts or [None] * self.n_layers)]
+        with _DeviceGuard(dev):
+            self.params = torch.empty(n, dtype=_F, device=dev)
+            check(L.ptt_sa_pack_params(self.C, self.n_layers, self.h_dims, arr(ws), arr(scales), arr(shifts),
+                                       _ptr(self.params), _stream()), "ptt_sa_pack_params")
+            torch.cuda.current_stream().synchronize()   # ws/scales/shifts temporaries may die after return
+        self.cout = dims[-1]
+
+    def workspace_bytes(self, B, M, ns):
+        return _lib.lib().ptt_sa_mlp_workspace_bytes(B, M, ns, self.C, self.n_layers, self.h_dims)
+
+
+def sa_mlp_fwd(packed, xyz, feats_pm, new_xyz, idx, radius, normalize_xyz, want_pm=True, want_cm=True, workspace=None):
+    """xyz (B,N,3), feats_pm (B,N,ldf)|None, new_xyz (B,M,3), idx (B,M,ns) -> out_pm (B,M,Cout), out_cm (B,Cout,M)."""
+    _req(xyz, _F, 3, "xyz"), _req(new_xyz, _F, 3, "new_xyz"), _req(idx, _I, 3, "idx")
+    dev = _same_device(xyz, new_xyz, idx, feats_pm)
+    B, N, _ = xyz.shape
+    _, M, ns = idx.shape
+    ldf = 0
+    if packed.C > 0:
+        _req(feats_pm, _F, 3, "feats_pm")
+        ldf = feats_pm.shape[2]
+        if feats_pm.shape[0] != B or feats_pm.shape[1] != N or ldf < packed.C:
+            raise PttError("sa_mlp_fwd: feats_pm must be (B,N,ld>=C)")
+    L = _lib.lib()
+    with _DeviceGuard(dev):
+        out_pm = torch.empty(B, M, packed.cout, dtype=_F, device=dev) if want_pm else None
+        out_cm = torch.empty(B, packed.cout, M, dtype=_F, device=dev) if want_cm else None
+        ws_bytes = packed.workspace_bytes(B, M, ns)
+        ws = workspace if workspace is not None else _workspace(ws_bytes, dev)
+        check(L.ptt_sa_mlp_fwd(_ptr(xyz), _ptr(feats_pm) if packed.C > 0 else None, ldf, _ptr(new_xyz), _ptr(idx), B, N, M,
+                               ns, packed.C, float(radius), int(bool(normalize_xyz)), packed.n_layers, packed.h_dims,
+                               _ptr(packed.params), _ptr(out_pm), packed.cout, _ptr(out_cm), _ptr(ws),
+                               ws.numel() * 4, _stream()), "ptt_sa_mlp_fwd")
+    return out_pm, out_cm
+
+
+TRANSFORMER_KEYS = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc_delta.0.weight", "fc_delta.0.bias",
+                    "fc_delta.2.weight", "fc_delta.2.bias", "fc_gamma.0.weight", "fc_gamma.0.bias",
+                    "fc_gamma.2.weight", "fc_gamma.2.bias", "w_qs.weight", "w_ks.weight", "w_vs.weight")
+
+
+class PackedTransformer:
+    """TransformerBlock parameters (state_dict keys of variants.py:129-147) packed for ptt_transformer_block_fwd."""
+
+    def __init__(self, sd, k, variant=0):
+        ts = [_req(sd[key].contiguous(), _F, sd[key].dim(), key) for key in TRANSFORMER_KEYS]
+        self.d_model, self.d_points = ts[0].shape
+        self.k = int(k)
+        self.variant = int(variant)
+        dev = ts[0].device
+        L = _lib.lib()
+        with _DeviceGuard(dev):
+            self.params = torch.empty(L.ptt_transformer_params_floats(self.d_points, self.d_model), dtype=_F, device=dev)
+            check(L.ptt_transformer_pack_params(self.d_points, self.d_model, *[_ptr(t) for t in ts], _ptr(self.params),
+                                                _stream()), "ptt_transformer_pack_params")
+            torch.cuda.current_stream().synchronize()
+
+    def workspace_bytes(self, B, n):
+        return _lib.lib().ptt_transformer_block_workspace_bytes(B, n, self.k, self.d_points, self.d_model)
+
+
+def transformer_block_fwd(packed, xyz, features, knn_idx=None, want_attn=False, workspace=None):
+    """xyz (B,n,3), features (B,n,d_points) -> out (B,n,d_points) [, attn (B,n,k,d_model)]."""
+    _req(xyz, _F, 3, "xyz"), _req(features, _F, 3, "features")
+    dev = _same_device(xyz, features, knn_idx)
+    B, n, _ = xyz.shape
+    if tuple(features.shape) != (B, n, packed.d_points):
+        raise PttError("transformer_block_fwd: features must be (B,n,%d)" % packed.d_points)
+    if knn_idx is not None:
+        _req(knn_idx, _I, 3, "knn_idx")
+    L = _lib.lib()
+    with _DeviceGuard(dev):
+        out = torch.empty(B, n, packed.d_points, dtype=_F, device=dev)
+        attn = torch.empty(B, n, packed.k, packed.d_model, dtype=_F, device=dev) if want_attn else None
+        ws_bytes = packed.workspace_bytes(B, n)
+        ws = workspace if workspace is not None else _workspace(ws_bytes, dev)
+        check(L.ptt_transformer_block_fwd(_ptr(xyz), _ptr(features), B, n, packed.k, packed.d_points, packed.d_model,
+                                          packed.variant, _ptr(packed.params), _ptr(knn_idx), _ptr(out), _ptr(attn),
+                                          _ptr(ws), ws.numel() * 4, _stream()), "ptt_transformer_block_fwd")
+    return (out, attn) if want_attn else out

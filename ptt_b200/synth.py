@@ -112,7 +112,7 @@ def fill_state_dict(state_dict, seed=0):
     (in this container) and the B200 module (on the GPU box) receive identical parameters."""
     out = {}
     for key, t in state_dict.items():
-        shape = tuple(t.shape)
+        shape = tuple(t) if isinstance(t, (tuple, list)) else tuple(t.shape)
         rs = np.random.RandomState(_key_seed(seed, key))
         leaf = key.rsplit(".", 1)[-1]
         if leaf == "num_batches_tracked":
@@ -129,6 +129,65 @@ def fill_state_dict(state_dict, seed=0):
         else:  # biases, norm shifts
             out[key] = (0.1 * rs.standard_normal(shape)).astype(np.float32)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# state_dict layouts (key -> shape) of the reference's hot modules; used to build
+# parameter sets on the GPU box, where the reference tree does not exist.
+# ------------------------------------------------------------------------------------------------
+def sa_layout(mlp, use_xyz=True, prefix=""):
+    """PointnetSAModuleVotes.state_dict() (pointnet2_modules.py:51-54, pytorch_utils.py:12-36)."""
+    spec = list(mlp)
+    if use_xyz:
+        spec[0] += 3
+    sd = {}
+    for i in range(len(spec) - 1):
+        p = "%smlp_module.layer%d." % (prefix, i)
+        sd[p + "conv.weight"] = (spec[i + 1], spec[i], 1, 1)
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            sd[p + "normlayer.bn." + k] = (spec[i + 1],)
+        sd[p + "normlayer.bn.num_batches_tracked"] = ()
+    return sd
+
+
+def transformer_layout(cls, dp, dm, prefix=""):
+    """state_dict() of the transformer_block/variants.py classes."""
+    sd = {}
+
+    def lin(name, i, o, bias=True):
+        sd[prefix + name + ".weight"] = (o, i)
+        if bias:
+            sd[prefix + name + ".bias"] = (o,)
+
+    if cls == "TransformerBlockMLP":
+        lin("fc1.0", dp, dm), lin("fc1.2", dm, dm), lin("fc2.0", dm, dm), lin("fc2.2", dm, dp)
+    else:
+        lin("fc1", dp, dm), lin("fc2", dm, dp)
+    lin("fc_delta.0", 3, dm), lin("fc_delta.2", dm, dm)
+    if cls != "TransformerBlockSTD":
+        lin("fc_gamma.0", dm, dm), lin("fc_gamma.2", dm, dm)
+    lin("w_qs", dm, dm, False), lin("w_ks", dm, dm, False), lin("w_vs", dm, dm, False)
+    return sd
+
+
+def hot_path_layout():
+    """The hot-path part of a PTT tracker's state_dict under tools/cfgs/kitti_models/ptt.yaml."""
+    sd = {}
+    for l, mlp in enumerate(([0, 64, 64, 128], [128, 128, 128, 256], [256, 128, 128, 256])):
+        sd.update(sa_layout(mlp, prefix="backbone_3d.SA_modules.%d." % l))
+    sd["backbone_3d.cov_final.weight"] = (256, 256, 1)
+    sd["backbone_3d.cov_final.bias"] = (256,)
+    sd.update(transformer_layout("TransformerBlock", 256, 512, "centroid_voting_head.transformer_block."))
+    sd.update(sa_layout([257, 256, 256, 256], prefix="box_voting_head.vote_aggregation."))
+    sd.update(transformer_layout("TransformerBlock", 256, 512, "box_voting_head.transformer_block."))
+    return sd
+
+
+def hot_path_state_dict(seed=0):
+    """Filled hot-path parameters as torch CPU tensors."""
+    import torch
+
+    return {k: torch.from_numpy(v) for k, v in fill_state_dict(hot_path_layout(), seed).items()}
 
 
 def load_filled(module, seed=0):

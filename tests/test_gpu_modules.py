@@ -1,0 +1,190 @@
+"""GPU parity: the fused SA layer, the transformer block and the whole hot path vs (a) the committed golden
+fixtures the REFERENCE's own modules produced (tests/golden/make_golden.py) and (b) the CPU oracle port.
+
+Tolerances: indices bit-exact; fp32 features within 1e-4 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import t
+from oracle import cops, torch_port
+from ptt_b200 import hotpath, modules, ops, synth
+from test_oracle_golden import SA_CASES, TR_CASES, sa_state_dict, transformer_state_dict
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+FP_TOL = dict(rtol=1e-4, atol=1e-4)
+
+
+def g(a):
+    if isinstance(a, np.ndarray):
+        a = t(a)
+    return a.to(DEV).contiguous()
+
+
+def filled(sd_template, seed):
+    return {k: t(v) for k, v in synth.fill_state_dict(sd_template, seed=seed).items()}
+
+
+@pytest.mark.parametrize("name", list(SA_CASES))
+def test_sa_module_vs_reference_fixture(golden, name):
+    gd = golden("sa_module.npz")
+    i = list(SA_CASES).index(name)
+    n, cin, mlp, npoint, radius, ns, method = SA_CASES[name]
+    mod = modules.PointnetSAModuleVotes(mlp=list(mlp), radius=radius, nsample=ns, use_xyz=True, normalize_xyz=True,
+                                        sample_method=method)
+    mod.load_state_dict(filled(sa_state_dict(mlp), 10 + i))
+    mod = mod.to(DEV).eval()
+    feats = g(synth.features((2, cin, n), seed=30 + i)) if cin else None
+    with torch.no_grad():
+        new_xyz, new_feats, inds = mod(g(gd[name + "/xyz"]), feats, npoint)
+    assert inds.dtype == torch.int64
+    assert np.array_equal(inds.cpu().numpy(), gd[name + "/inds"])
+    assert np.array_equal(new_xyz.cpu().numpy(), gd[name + "/new_xyz"])
+    np.testing.assert_allclose(new_feats.cpu().numpy(), gd[name + "/new_features"], **FP_TOL)
+
+
+@pytest.mark.parametrize("name", ["centroid", "box", "small", "offset"])
+def test_transformer_vs_reference_fixture(golden, name):
+    gd = golden("transformer.npz")
+    i = list(TR_CASES).index(name)
+    cls, n, dp, dm, k = TR_CASES[name]
+    mod = getattr(modules, cls)(dp, dm, k, heads=1, layers=1)
+    mod.load_state_dict(filled(transformer_state_dict(cls, dp, dm), 40 + i))
+    mod = mod.to(DEV).eval()
+    xyz = gd[name + "/xyz"]
+    f = synth.features((2, n, dp), seed=60 + i)
+    assert synth.crc(f) == int(gd[name + "/features_crc"])
+    with torch.no_grad():
+        res, attn = mod(g(xyz), g(f))
+    np.testing.assert_allclose(res.cpu().numpy(), gd[name + "/res"], **FP_TOL)
+    np.testing.assert_allclose(attn[:, :4].cpu().numpy(), gd[name + "/attn_head"], **FP_TOL)
+
+
+def test_transformer_with_exact_ties_matches_port():
+    # duplicate-heavy cloud: kNN ties are resolved lowest-index-first on both sides
+    cls, n, dp, dm, k = "TransformerBlock", 64, 32, 64, 16
+    sd = filled(transformer_state_dict(cls, dp, dm), 7)
+    xyz = synth.make_clouds(3, n, 9, "sparse")
+    f = synth.features((3, n, dp), seed=9)
+    want, want_attn = torch_port.transformer_block(sd, t(xyz), t(f), k)
+    packed = ops.PackedTransformer({kk: g(v) for kk, v in sd.items()}, k)
+    got, attn = ops.transformer_block_fwd(packed, g(xyz), g(f), want_attn=True)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), **FP_TOL)
+    np.testing.assert_allclose(attn.cpu().numpy(), want_attn.numpy(), **FP_TOL)
+
+
+def test_sa_layer_random_shapes_vs_port():
+    cases = [(300, 7, [7, 16, 32], 100, 0.5, 12, "fps"), (64, 0, [0, 8], 64, 0.9, 3, "fps"),
+             (512, 64, [64, 64, 64, 64, 96], 128, 0.4, 32, "sequence")]
+    for i, (n, cin, mlp, npoint, radius, ns, method) in enumerate(cases):
+        sd = filled(sa_state_dict(mlp), 90 + i)
+        xyz = synth.make_clouds(2, n, 91 + i, "sparse" if i == 0 else "dense")
+        feats = synth.features((2, cin, n), seed=92 + i) if cin else None
+        w_xyz, w_feats, w_inds = torch_port.sa_module_votes(sd, t(xyz), t(feats) if cin else None, npoint, radius, ns,
+                                                             method, True, True)
+        mod = modules.PointnetSAModuleVotes(mlp=list(mlp), radius=radius, nsample=ns, normalize_xyz=True,
+                                            sample_method=method)
+        mod.load_state_dict(sd)
+        mod = mod.to(DEV).eval()
+        with torch.no_grad():
+            new_xyz, new_feats, inds = mod(g(xyz), g(feats) if cin else None, npoint)
+        assert np.array_equal(inds.cpu().numpy(), w_inds.numpy())
+        assert np.array_equal(new_xyz.cpu().numpy(), w_xyz.numpy())
+        np.testing.assert_allclose(new_feats.cpu().numpy(), w_feats.numpy(), **FP_TOL)
+
+
+def test_sa_module_training_mode_matches_port_forward_and_grads():
+    n, cin, mlp, npoint, radius, ns = 128, 16, [16, 32, 48], 40, 0.6, 8
+    sd = filled(sa_state_dict(mlp), 123)
+    xyz = synth.make_clouds(3, n, 124, "dense", role="template")
+    feats = synth.features((3, cin, n), seed=125)
+    # oracle side: CPU autograd through the port (batch statistics: training=True)
+    sd_cpu = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    xyz_c = t(xyz).clone().requires_grad_(True)
+    f_c = t(feats).clone().requires_grad_(True)
+    w_xyz, w_feats, _ = _port_sa_training(sd_cpu, xyz_c, f_c, npoint, radius, ns)
+    (w_feats.square().sum() + w_xyz.sum()).backward()
+
+    mod = modules.PointnetSAModuleVotes(mlp=list(mlp), radius=radius, nsample=ns, normalize_xyz=True, sample_method="fps")
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV).train()
+    xyz_g = g(xyz).requires_grad_(True)
+    f_g = g(feats).requires_grad_(True)
+    new_xyz, new_feats, _ = mod(xyz_g, f_g, npoint)
+    (new_feats.square().sum() + new_xyz.sum()).backward()
+    np.testing.assert_allclose(new_feats.detach().cpu().numpy(), w_feats.detach().numpy(), rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(f_g.grad.cpu().numpy(), f_c.grad.numpy(), rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(xyz_g.grad.cpu().numpy(), xyz_c.grad.numpy(), rtol=1e-3, atol=2e-3)
+    gw = mod.mlp_module.layer0.conv.weight.grad.cpu().numpy()
+    np.testing.assert_allclose(gw, sd_cpu["mlp_module.layer0.conv.weight"].grad.numpy(), rtol=1e-3, atol=2e-3)
+
+
+def _port_sa_training(sd, xyz, feats, npoint, radius, ns):
+    """The port's SA layer with differentiable gathers (torch indexing) for the CPU side of the grad test."""
+    import torch.nn.functional as F
+    inds = cops.furthest_point_sampling(xyz.detach().contiguous(), npoint).long()
+    new_xyz = torch.gather(xyz, 1, inds[:, :, None].expand(-1, -1, 3))
+    idx = cops.ball_query(new_xyz.detach().contiguous(), xyz.detach().contiguous(), radius, ns).long()
+    B, M, K = idx.shape
+    flat = idx.reshape(B, 1, M * K)
+    gx = torch.gather(xyz.transpose(1, 2), 2, flat.expand(-1, 3, -1)).reshape(B, 3, M, K)
+    gx = (gx - new_xyz.transpose(1, 2).unsqueeze(-1)) / radius
+    gf = torch.gather(feats, 2, flat.expand(-1, feats.shape[1], -1)).reshape(B, -1, M, K)
+    y = torch.cat([gx, gf], 1)
+    i = 0
+    while "mlp_module.layer%d.conv.weight" % i in sd:
+        p = "mlp_module.layer%d." % i
+        y = F.conv2d(y, sd[p + "conv.weight"])
+        y = F.batch_norm(y, None, None, sd[p + "normlayer.bn.weight"], sd[p + "normlayer.bn.bias"], training=True)
+        y = F.relu(y)
+        i += 1
+    return new_xyz, y.max(dim=3)[0], inds
+
+
+@pytest.mark.parametrize("name", ["dense", "sparse"])
+def test_hot_path_vs_reference_fixture(golden, name):
+    gd = golden("hot_path.npz")
+    sd = synth.hot_path_state_dict(0)
+    hp = hotpath.HotPath(sd, device=DEV)
+    out = hp(g(gd[name + "/search"]), g(gd[name + "/template"]))
+    torch.cuda.synchronize()
+    for k in ("search_inds", "template_inds"):
+        assert np.array_equal(out[k].cpu().numpy(), gd[name + "/" + k]), k
+    for k in ("search_seeds", "template_seeds", "box_centers"):
+        assert np.array_equal(out[k].cpu().numpy(), gd[name + "/" + k]), k
+    for k in ("search_feats", "template_feats", "centroid_feats", "box_sa_feats", "box_feats"):
+        np.testing.assert_allclose(out[k].cpu().numpy(), gd[name + "/" + k], err_msg=k, **FP_TOL)
+
+
+def test_hot_path_full_batch_properties():
+    """BASELINE config 2 size (B=48, N=1024/512): size-independent properties + a per-frame spot check
+    against the oracle on 2 of the 48 frames."""
+    B = 48
+    sd = synth.hot_path_state_dict(0)
+    hp = hotpath.HotPath(sd, device=DEV)
+    search = synth.make_clouds(B, 1024, 500, "dense")
+    template = synth.make_clouds(B, 512, 501, "dense", role="template")
+    out = hp(g(search), g(template))
+    torch.cuda.synchronize()
+    inds = out["search_inds"].cpu().numpy()
+    assert inds.shape == (B, 128) and (inds[:, 0] == 0).all()
+    assert all(len(set(r.tolist())) == 128 for r in inds)          # distinct points -> distinct samples
+    seeds = out["search_seeds"].cpu().numpy()
+    assert np.array_equal(seeds, np.take_along_axis(search, inds[:, :, None], 1))
+    for k, v in out.items():
+        assert torch.isfinite(v.float()).all(), k
+    # batch independence: frames 5 and 41 alone give the same answer as inside the batch of 48
+    sub = hp(g(search[[5, 41]]), g(template[[5, 41]]))
+    for k in out:
+        a, b = out[k][[5, 41]].cpu().numpy(), sub[k].cpu().numpy()
+        if a.dtype.kind == "i":
+            assert np.array_equal(a, b), k
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-5, err_msg=k)
+    want = torch_port.hot_path_frame(sd, t(search[[5, 41]]), t(template[[5, 41]]))
+    for k in ("search_inds", "template_inds"):
+        assert np.array_equal(sub[k].cpu().numpy(), want[k].numpy()), k
+    for k in ("search_feats", "template_feats", "centroid_feats", "box_sa_feats", "box_feats"):
+        np.testing.assert_allclose(sub[k].cpu().numpy(), want[k].numpy(), err_msg=k, **FP_TOL)
