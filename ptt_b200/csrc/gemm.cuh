@@ -11,8 +11,9 @@ struct PttGemmArgs {
   int ldx = 0;
   const int* a_rows = nullptr;  // optional: output row r reads x row a_rows[r]
   int R = 0, K = 0;
-  const float* wt = nullptr;
+  const float* wt = nullptr;   // fp32 transposed weight (K rows of ldw floats): the CUDA-core path
   int ldw = 0;
+  const void* wimg = nullptr;  // fp16 hi/lo UMMA image of the same weight (ptt_tc_pack_weight): the tcgen05 path
   int N = 0;
   const float* scale = nullptr;  // nullptr = 1
   const float* shift = nullptr;  // nullptr = 0   (bias or folded BatchNorm shift)
@@ -23,7 +24,19 @@ struct PttGemmArgs {
   int ldy = 0;
 };
 
+// Runs on the tcgen05 path when `wimg` is set and the A operand qualifies (16-byte aligned rows), else on the
+// CUDA-core path.  Both produce fp32-class results (tests compare them against each other on the device).
 int ptt_gemm_launch(const PttGemmArgs& a, cudaStream_t st);
+int ptt_gemm_launch_ffma(const PttGemmArgs& a, cudaStream_t st);
+
+// tcgen05 path (tc_gemm.cu)
+size_t ptt_tc_weight_halves(int K, int Cout);   // size of the fp16 image, in 2-byte units (multiple of 8192)
+// src(c, k) = w[c * ld_c + k * ld_k]: (Cout, K) row-major weight -> ld_c = K, ld_k = 1; transposed (K, ldw) image -> ld_c = 1, ld_k = ldw
+int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout, int K, void* img, cudaStream_t st);
+bool ptt_tc_gemm_supported(const PttGemmArgs& a);
+int ptt_tc_gemm_launch(const PttGemmArgs& a, const void* wimg, cudaStream_t st);
+// floats occupied by the tcgen05 image of a (Cout, K) weight
+static inline size_t ptt_tc_weight_floats(int K, int Cout) { return ptt_tc_weight_halves(K, Cout) / 2; }
 
 // nn.Linear (Cout,K) weight [+bias] -> transposed image (K+1 rows x ldw, last row = bias), zero padded
 int ptt_linear_pack_launch(const float* weight, const float* bias, int K, int Cout, float* params, cudaStream_t st);

@@ -116,7 +116,17 @@ __global__ void linear_pack_kernel(const float* __restrict__ w, const float* __r
 
 }  // namespace
 
+static int g_force_ffma = 0;
+// Test hook (not in the public header): 1 = run every contraction on the CUDA-core path.
+extern "C" __attribute__((visibility("default"))) void ptt_debug_force_ffma(int on) { g_force_ffma = on; }
+
 int ptt_gemm_launch(const PttGemmArgs& a, cudaStream_t st) {
+  if (a.R <= 0 || a.N <= 0) return PTT_OK;
+  if (a.wimg != nullptr && !g_force_ffma && ptt_tc_gemm_supported(a)) return ptt_tc_gemm_launch(a, a.wimg, st);
+  return ptt_gemm_launch_ffma(a, st);
+}
+
+int ptt_gemm_launch_ffma(const PttGemmArgs& a, cudaStream_t st) {
   if (a.R <= 0 || a.N <= 0) return PTT_OK;
   dim3 grid(ceil_div(a.R, BM), ceil_div(a.N, BN));
   const bool vec = (a.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15u) == 0);
@@ -140,12 +150,14 @@ int ptt_linear_pack_launch(const float* weight, const float* bias, int K, int Co
   const int ldw = ptt_linear_ldw(Cout);
   cudaError_t e = cudaMemsetAsync(params, 0, (size_t)(K + 1) * ldw * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
-  return ptt_linear_pack_cols(weight, bias, K, Cout, ldw, 0, params, st);
+  int rc = ptt_linear_pack_cols(weight, bias, K, Cout, ldw, 0, params, st);
+  if (rc != PTT_OK) return rc;
+  return ptt_tc_pack_weight(weight, K, 1, Cout, K, params + (size_t)(K + 1) * ldw, st);
 }
 
 extern "C" size_t ptt_linear_params_floats(int K, int Cout) {
   if (K < 0 || Cout <= 0) return 0;
-  return (size_t)(K + 1) * ptt_linear_ldw(Cout);
+  return (size_t)(K + 1) * ptt_linear_ldw(Cout) + ptt_tc_weight_floats(K, Cout);
 }
 
 extern "C" int ptt_linear_pack(const float* weight, const float* bias, int K, int Cout, float* params,
@@ -163,6 +175,7 @@ extern "C" int ptt_linear_fwd(const float* x, int ldx, int R, int K, const float
   a.x = x; a.ldx = ldx; a.R = R; a.K = K;
   a.wt = params; a.ldw = ptt_linear_ldw(Cout); a.N = Cout;
   a.shift = params + (size_t)K * a.ldw;
+  a.wimg = params + (size_t)(K + 1) * a.ldw;
   a.relu = relu;
   a.residual = residual; a.ldr = ldr;
   a.y = y; a.ldy = ldy;

@@ -19,7 +19,7 @@ struct SaLayout {
   int n_layers;
   int dims[SA_MAX_LAYERS + 1];
   int ldw[SA_MAX_LAYERS];
-  size_t wt[SA_MAX_LAYERS], scale[SA_MAX_LAYERS], shift[SA_MAX_LAYERS];
+  size_t wt[SA_MAX_LAYERS], scale[SA_MAX_LAYERS], shift[SA_MAX_LAYERS], wimg[SA_MAX_LAYERS];
   size_t total;
 };
 
@@ -40,6 +40,8 @@ bool sa_layout(int C, int n_layers, const int* h_dims, SaLayout* L) {
     off += L->ldw[l];
     L->shift[l] = off;
     off += L->ldw[l];
+    L->wimg[l] = off;      // fp16 hi/lo tensor-core image of the same (permuted) weight
+    off += ptt_tc_weight_floats(L->dims[l], L->dims[l + 1]);
   }
   L->total = off;
   return true;
@@ -128,6 +130,8 @@ extern "C" int ptt_sa_pack_params(int C, int n_layers, const int* h_dims, const 
     sa_pack_vec_kernel<<<ceil_div(L.ldw[l], 256), 256, 0, st>>>(h_scale ? h_scale[l] : nullptr,
                                                                  h_shift ? h_shift[l] : nullptr, L.dims[l + 1], L.ldw[l],
                                                                  params + L.scale[l], params + L.shift[l]); PTT_LAUNCHED();
+    int rc = ptt_tc_pack_weight(params + L.wt[l], 1, L.ldw[l], L.dims[l + 1], L.dims[l], params + L.wimg[l], st);
+    if (rc != PTT_OK) return rc;
   }
   return ptt_launch_status();
 }
@@ -193,6 +197,7 @@ extern "C" int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, con
     PttGemmArgs a;
     a.x = in; a.ldx = ld_in; a.R = (int)rows; a.K = L.dims[l];
     a.wt = params + L.wt[l]; a.ldw = L.ldw[l]; a.N = L.dims[l + 1];
+    a.wimg = params + L.wimg[l];
     a.scale = params + L.scale[l]; a.shift = params + L.shift[l]; a.relu = 1;
     a.y = H[l & 1]; a.ldy = W.ldh;
     int rc = ptt_gemm_launch(a, st);

@@ -1,0 +1,313 @@
+// Tensor-core row-block contraction for sm_100a (tcgen05 + TMEM), fp32 in / fp32 out at fp32-class accuracy.
+//
+//   y[r, 0:N] = act( scale[c] * (x[row(r), 0:K] . W[c, 0:K]) + shift[c] ) (+ residual[r, c])
+//
+// fp32-within-1e-4 on 16-bit tensor-core inputs: every operand is split into two fp16 halves (x = hi + lo,
+// ~22 significant bits) and each K-step issues three MMAs into the same TMEM accumulator,
+//   hi.hi + lo.hi + hi.lo        (lo.lo ~ 2^-22 relative is dropped),
+// i.e. a K' = 3K fp16 contraction with an fp32 accumulator.  Weights are split once at pack time into the
+// UMMA canonical K-major SWIZZLE_128B image (so the TMA engine streams them with plain bulk copies);
+// activations are split on the fly by the producer warps while they stage the A tile in shared memory.
+//
+// CTA = 128 output rows x BN output columns; warp roles:
+//   warps 0-3  A producers (global fp32 rows, optional row gather -> fp16 hi/lo -> swizzled smem), then
+//              epilogue (TMEM -> registers -> scale/shift/ReLU/residual -> global)
+//   warp  4    weight loader: cp.async.bulk (TMA engine) of pre-swizzled 8 KB blocks, mbarrier complete_tx
+//   warp  5    TMEM allocation + the single thread that issues tcgen05.mma / tcgen05.commit
+// K is consumed in 64-wide blocks through a 2-4 stage ring of (A hi, A lo, B hi, B lo) tiles.
+#include "gemm.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TBM = 128;       // rows per CTA
+constexpr int TBK = 64;        // K per stage = one 128-byte swizzle row of fp16
+constexpr int TC_THREADS = 192;
+constexpr uint32_t A_HALF_BYTES = TBM * TBK * 2;      // 16 KB
+constexpr uint32_t W_BLOCK_BYTES = 64 * TBK * 2;      // 8 KB: 64 weight rows x 64 k
+
+template <int BN>
+struct TcCfg {
+  static constexpr uint32_t B_HALF_BYTES = BN * TBK * 2;
+  static constexpr uint32_t STAGE_BYTES = 2 * A_HALF_BYTES + 2 * B_HALF_BYTES;
+  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers, table*/;
+};
+
+struct TcParams {
+  PttGemmArgs g;
+  const __half* wimg;   // packed weight image
+  int n_wblocks;        // 64-row weight blocks available (Np / 64)
+  int k_blocks;         // Kp / 64
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ctrl = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(ctrl);           // [STAGES]
+  uint64_t* full_b = full_a + STAGES;                              // [STAGES]
+  uint64_t* empty = full_b + STAGES;                               // [STAGES]
+  uint64_t* accum_full = empty + STAGES;                           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  int* s_row = reinterpret_cast<int*>(ctrl + 256);                 // [128] source row per tile row, -1 = none
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * TBM;
+  const int ntile = blockIdx.y;
+  const PttGemmArgs& g = p.g;
+  const int KB = p.k_blocks;
+
+  if (tid < TBM) {
+    const int r = row0 + tid;
+    s_row[tid] = r < g.R ? (g.a_rows ? g.a_rows[r] : r) : -1;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(&full_a[s], TBM);
+      tc::mbar_init(&full_b[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    tc::mbar_init(accum_full, 1);
+    tc::mbar_init_fence();
+  }
+  if (warp == 5) tc::tmem_alloc(tmem_slot, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ A producers
+    const int c4 = tid & 15;          // float4 column within the 64-wide k block
+    const int rsub = tid >> 4;        // 0..7
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < KB; ++kb) {
+      tc::mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* a_hi = smem + stage * Cfg::STAGE_BYTES;
+      uint8_t* a_lo = a_hi + A_HALF_BYTES;
+      const int k = kb * TBK + c4 * 4;
+      float4 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int src = s_row[i * 8 + rsub];
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src >= 0 && k < g.K) {
+          const float* ptr = g.x + (size_t)src * g.ldx + k;
+          if (k + 3 < g.K) {
+            v[i] = __ldg(reinterpret_cast<const float4*>(ptr));
+          } else {
+            v[i].x = __ldg(ptr);
+            if (k + 1 < g.K) v[i].y = __ldg(ptr + 1);
+            if (k + 2 < g.K) v[i].z = __ldg(ptr + 2);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = i * 8 + rsub;
+        __half h[4], l[4];
+        tc::split_f16(v[i].x, h[0], l[0]);
+        tc::split_f16(v[i].y, h[1], l[1]);
+        tc::split_f16(v[i].z, h[2], l[2]);
+        tc::split_f16(v[i].w, h[3], l[3]);
+        const uint32_t off = tc::sw128_offset(r, c4 >> 1) + ((c4 & 1) << 3);
+        uint2 ph, pl;
+        ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+        ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+        pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+        pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+        *reinterpret_cast<uint2*>(a_hi + off) = ph;
+        *reinterpret_cast<uint2*>(a_lo + off) = pl;
+      }
+      tc::fence_proxy_async_smem();
+      tc::mbar_arrive(&full_a[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    // ------------------------------------------------------------ epilogue
+    tc::mbar_wait(accum_full, 0);
+    tc::tc_fence_after();
+    const int r = row0 + warp * 32 + lane;
+    const bool row_ok = r < g.R;
+    const bool vec_y = (g.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.y) & 15u) == 0);
+    const bool vec_r = g.residual && (g.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.residual) & 15u) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int col0 = ntile * BN + c0;
+      if (col0 >= g.N) break;       // warp-uniform
+      float v[32];
+      tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (!row_ok) continue;
+      float* yrow = g.y + (size_t)r * g.ldy + col0;
+      const float* rrow = g.residual ? g.residual + (size_t)r * g.ldr + col0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = col0 + j + u;
+          float t = v[j + u];
+          if (c < g.N) {
+            if (g.scale) t *= __ldg(g.scale + c);
+            if (g.shift) t += __ldg(g.shift + c);
+            if (g.relu) t = fmaxf(t, 0.f);
+          }
+          o[u] = t;
+        }
+        if (col0 + j + 3 < g.N) {
+          if (rrow) {
+            if (vec_r) {
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + j));
+              o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) o[u] += __ldg(rrow + j + u);
+            }
+          }
+          if (vec_y) {
+            *reinterpret_cast<float4*>(yrow + j) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) yrow[j + u] = o[u];
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (col0 + j + u < g.N) yrow[j + u] = o[u] + (rrow ? __ldg(rrow + j + u) : 0.f);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ weight loader (TMA engine)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      constexpr int SUB = BN / 64;
+      int nsub = p.n_wblocks - ntile * SUB;
+      nsub = nsub > SUB ? SUB : nsub;
+      for (int kb = 0; kb < KB; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* b_hi = smem + stage * Cfg::STAGE_BYTES + 2 * A_HALF_BYTES;
+        uint8_t* b_lo = b_hi + Cfg::B_HALF_BYTES;
+        tc::mbar_arrive_expect_tx(&full_b[stage], (uint32_t)nsub * 2u * W_BLOCK_BYTES);
+        for (int j = 0; j < nsub; ++j) {
+          const size_t blk = ((size_t)(ntile * SUB + j) * KB + kb) * 2;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + blk * W_BLOCK_BYTES;
+          tc::bulk_g2s(b_hi + j * W_BLOCK_BYTES, src, W_BLOCK_BYTES, &full_b[stage]);
+          tc::bulk_g2s(b_lo + j * W_BLOCK_BYTES, src + W_BLOCK_BYTES, W_BLOCK_BYTES, &full_b[stage]);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t IDESC = tc::idesc_f16<false>(TBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        tc::mbar_wait(&full_a[stage], phase);
+        tc::mbar_wait(&full_b[stage], phase);
+        tc::tc_fence_after();
+        const uint32_t a_hi = tc::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t da_hi = tc::smem_desc_sw128(a_hi);
+        const uint64_t da_lo = tc::smem_desc_sw128(a_hi + A_HALF_BYTES);
+        const uint64_t db_hi = tc::smem_desc_sw128(a_hi + 2 * A_HALF_BYTES);
+        const uint64_t db_lo = tc::smem_desc_sw128(a_hi + 2 * A_HALF_BYTES + Cfg::B_HALF_BYTES);
+#pragma unroll
+        for (int k = 0; k < TBK / 16; ++k) {
+          const uint64_t adv = (uint64_t)(k * 2);   // 32 bytes per UMMA_K, in 16-byte units of the address field
+          tc::mma_f16(tmem_base, da_hi + adv, db_hi + adv, IDESC, (kb | k) != 0);
+          tc::mma_f16(tmem_base, da_lo + adv, db_hi + adv, IDESC, 1);
+          tc::mma_f16(tmem_base, da_hi + adv, db_lo + adv, IDESC, 1);
+        }
+        tc::mma_commit(&empty[stage]);     // frees the stage once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc::mma_commit(accum_full);
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// nn.Linear-style weight (Cout, K) row-major fp32  ->  fp16 hi/lo image of 8 KB blocks:
+//   block (nb, kb, half) at ((nb * KB + kb) * 2 + half) * 8 KB; inside, row r (0..63) / 16-byte chunk c at
+//   sw128_offset(r, c); rows >= Cout and k >= K are zero.
+//   src(c, k) = w[c * ld_c + k * ld_k]   (so a transposed (K, ldw) image can be the source too)
+__global__ void tc_pack_weight_kernel(const float* __restrict__ w, long long ld_c, long long ld_k, int Cout, int K, int NB,
+                                      int KB, __half* __restrict__ img) {
+  const long long total = (long long)NB * KB * 64 * 8;   // (block, row, chunk)
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e & 7);
+    const int r = (int)((e >> 3) & 63);
+    const long long blk = e >> 9;
+    const int kb = (int)(blk % KB), nb = (int)(blk / KB);
+    const int n = nb * 64 + r;
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = kb * 64 + c * 8 + u;
+      const float x = (n < Cout && k < K) ? w[(long long)n * ld_c + (long long)k * ld_k] : 0.f;
+      tc::split_f16(x, hi[u], lo[u]);
+    }
+    uint8_t* base = reinterpret_cast<uint8_t*>(img) + (size_t)blk * 2 * W_BLOCK_BYTES + tc::sw128_offset(r, c);
+    *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + W_BLOCK_BYTES) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+template <int BN>
+int tc_launch(const TcParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  auto kern = tc_gemm_kernel<BN>;
+  static bool configured = false;   // attribute is per function, idempotent; racing threads set the same value
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  dim3 grid(ceil_div(p.g.R, TBM), ceil_div(p.g.N, BN));
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p); PTT_LAUNCHED();
+  return ptt_launch_status();
+}
+
+}  // namespace
+
+size_t ptt_tc_weight_halves(int K, int Cout) {
+  return (size_t)ceil_div(Cout, 64) * ceil_div(K, 64) * 2 * (W_BLOCK_BYTES / 2);
+}
+
+int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout, int K, void* img, cudaStream_t st) {
+  const int NB = ceil_div(Cout, 64), KB = ceil_div(K, 64);
+  const long long total = (long long)NB * KB * 512;
+  tc_pack_weight_kernel<<<(unsigned)llmin_((total + 255) / 256, 2048), 256, 0, st>>>(w, ld_c, ld_k, Cout, K, NB, KB,
+                                                                                      static_cast<__half*>(img)); PTT_LAUNCHED();
+  return ptt_launch_status();
+}
+
+bool ptt_tc_gemm_supported(const PttGemmArgs& a) {
+  return a.R > 0 && a.N > 0 && a.K > 0 && (a.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15u) == 0) &&
+         round_up(a.K, 4) <= a.ldx;
+}
+
+int ptt_tc_gemm_launch(const PttGemmArgs& a, const void* wimg, cudaStream_t st) {
+  TcParams p;
+  p.g = a;
+  p.wimg = static_cast<const __half*>(wimg);
+  p.n_wblocks = ceil_div(a.N, 64);
+  p.k_blocks = ceil_div(a.K, 64);
+  if (a.N <= 64) return tc_launch<64>(p, st);
+  if (a.N <= 128) return tc_launch<128>(p, st);
+  return tc_launch<256>(p, st);
+}

@@ -24,7 +24,12 @@ bool tr_layout(int dp, int dm, TrLayout* L) {
   if (dp < 1 || dm < 1) return false;
   L->dp = dp; L->dm = dm;
   size_t off = 0;
-  auto take = [&](int K, int Cout) { size_t o = off; off += align_up((size_t)(K + 1) * round_up(Cout, 4), 4); return o; };
+  // each image: transposed fp32 weight (K rows) + bias row, then the fp16 hi/lo tensor-core image
+  auto take = [&](int K, int Cout) {
+    size_t o = off;
+    off += align_up((size_t)(K + 1) * round_up(Cout, 4), 4) + ptt_tc_weight_floats(K, Cout);
+    return o;
+  };
   L->fc1 = take(dp, dm);
   L->qkv = take(dm, 3 * round_up(dm, 4));
   L->delta0 = take(3, dm);
@@ -159,6 +164,17 @@ extern "C" int ptt_transformer_pack_params(int d_points, int d_model, const floa
   if ((rc = ptt_linear_pack_cols(gamma0_w, gamma0_b, dm, dm, ld, 0, params + L.gamma0, st))) return rc;
   if ((rc = ptt_linear_pack_cols(gamma2_w, gamma2_b, dm, dm, ld, 0, params + L.gamma2, st))) return rc;
   if ((rc = ptt_linear_pack_cols(fc2_w, fc2_b, dm, dp, round_up(dp, 4), 0, params + L.fc2, st))) return rc;
+  // tensor-core images, built from the transposed fp32 images just written (src(c,k) = wt[k*ldw + c])
+  auto tc_pack = [&](size_t img, int K, int Cout) {
+    const int ldw = round_up(Cout, 4);
+    return ptt_tc_pack_weight(params + img, 1, ldw, Cout, K, params + img + (size_t)(K + 1) * ldw, st);
+  };
+  if ((rc = tc_pack(L.fc1, dp, dm))) return rc;
+  if ((rc = tc_pack(L.qkv, dm, 3 * ld))) return rc;
+  if ((rc = tc_pack(L.delta2, dm, dm))) return rc;
+  if ((rc = tc_pack(L.gamma0, dm, dm))) return rc;
+  if ((rc = tc_pack(L.gamma2, dm, dm))) return rc;
+  if ((rc = tc_pack(L.fc2, dm, dp))) return rc;
   return PTT_OK;
 }
 
@@ -208,6 +224,7 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
     g.x = in; g.ldx = ldin; g.R = (int)R; g.K = K;
     g.wt = params + img; g.ldw = ldw; g.N = Cout;
     g.shift = bias ? params + img + (size_t)K * ldw : nullptr;
+    g.wimg = params + img + (size_t)(K + 1) * ldw;
     g.relu = relu;
     g.residual = residual; g.ldr = ldr;
     g.y = y; g.ldy = ldy;

@@ -96,6 +96,9 @@ def test_sa_layer_random_shapes_vs_port():
 
 
 def test_sa_module_training_mode_matches_port_forward_and_grads():
+    # training mode runs torch's own Conv2d/BatchNorm (as the reference does); keep cuDNN in true fp32 for the comparison
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     n, cin, mlp, npoint, radius, ns = 128, 16, [16, 32, 48], 40, 0.6, 8
     sd = filled(sa_state_dict(mlp), 123)
     xyz = synth.make_clouds(3, n, 124, "dense", role="template")

@@ -192,6 +192,34 @@ def test_linear_vs_torch_fp32():
         np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4, atol=1e-4)   # north_star: fp32 within 1e-4
 
 
+@pytest.mark.parametrize("R,K,C", [(128, 64, 64), (1, 64, 8), (130, 64, 64), (1000, 260, 200), (4099, 132, 128),
+                                   (20000, 512, 512), (333, 512, 1536), (256, 256, 257), (64, 8, 300)])
+def test_tensor_core_linear_is_fp32_accurate(R, K, C):
+    """The tcgen05 path (fp16 hi/lo split, 3 MMAs per K-step) against float64, and against the CUDA-core path."""
+    import ctypes
+    from ptt_b200 import _lib
+    rs = np.random.RandomState(R + K + C)
+    x = (rs.standard_normal((R, K)) * np.exp(rs.uniform(-6, 6, size=(R, 1)))).astype(np.float32)   # rows spanning 5 decades
+    w = (rs.standard_normal((C, K)) / np.sqrt(K)).astype(np.float32)
+    b = rs.standard_normal(C).astype(np.float32)
+    res = rs.standard_normal((R, C)).astype(np.float32)
+    lin = ops.PackedLinear(g(w), g(b))
+    want = torch.relu(t(x).double() @ t(w).double().T + t(b).double()) + t(res).double()
+    got = lin(g(x), relu=True, residual=g(res)).cpu().double()
+    scale = (t(x).double().abs() @ t(w).double().abs().T) + 1.0       # conditioning of each dot product
+    err = ((got - want).abs() / scale).max().item()
+    assert err < 2e-6, err                                            # fp32-class: ~2^-22 relative to sum |a||b|
+    force = _lib.lib().ptt_debug_force_ffma
+    force.argtypes = [ctypes.c_int]
+    force(1)
+    try:
+        ffma = lin(g(x), relu=True, residual=g(res)).cpu().double()
+    finally:
+        force(0)
+    assert ((ffma - want).abs() / scale).max().item() < 2e-6
+    assert ((ffma - got).abs() / scale).max().item() < 2e-6
+
+
 def test_errors_are_raised_not_fatal():
     xyz = g(synth.make_clouds(1, 64, 1))
     with pytest.raises(RuntimeError):
