@@ -235,7 +235,7 @@ extern "C" size_t ptt_furthest_point_sampling_workspace_bytes(int B, int N, int 
 }
 
 // Tuning hook (not part of the public header): run FPS with an explicit (threads, points/thread).
-extern "C" int ptt_fps_variant(const float* xyz, int B, int N, int npoint, int* idx, float* new_xyz,
+extern "C" __attribute__((visibility("default"))) int ptt_fps_variant(const float* xyz, int B, int N, int npoint, int* idx, float* new_xyz,
                                int threads, int ppt, ptt_stream_t stream) {
   cudaStream_t st = as_stream(stream);
   if ((long long)threads * ppt < N) return PTT_ERR_UNSUPPORTED;

@@ -31,7 +31,7 @@ struct TcCfg {
   static constexpr uint32_t B_HALF_BYTES = BN * TBK * 2;
   static constexpr uint32_t STAGE_BYTES = 2 * A_HALF_BYTES + 2 * B_HALF_BYTES;
   static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers, table*/;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 4096 /*barriers, tables*/;
 };
 
 struct TcParams {
@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   uint64_t* accum_full = empty + STAGES;                           // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
   int* s_row = reinterpret_cast<int*>(ctrl + 256);                 // [128] source row per tile row, -1 = none
+  float* s_scale = reinterpret_cast<float*>(ctrl + 1024);          // [BN] epilogue scale of this CTA's columns
+  float* s_shift = reinterpret_cast<float*>(ctrl + 2048);          // [BN] epilogue shift
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TBM;
@@ -64,6 +66,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   if (tid < TBM) {
     const int r = row0 + tid;
     s_row[tid] = r < g.R ? (g.a_rows ? g.a_rows[r] : r) : -1;
+  }
+  for (int c = tid; c < BN; c += TC_THREADS) {
+    const int col = blockIdx.y * BN + c;
+    s_scale[c] = (g.scale && col < g.N) ? __ldg(g.scale + col) : 1.f;
+    s_shift[c] = (g.shift && col < g.N) ? __ldg(g.shift + col) : 0.f;
   }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -149,15 +156,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       for (int j = 0; j < 32; j += 4) {
         float o[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = col0 + j + u;
-          float t = v[j + u];
-          if (c < g.N) {
-            if (g.scale) t *= __ldg(g.scale + c);
-            if (g.shift) t += __ldg(g.shift + c);
-            if (g.relu) t = fmaxf(t, 0.f);
-          }
-          o[u] = t;
+        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + j);
+        const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + j);
+        o[0] = fmaf(v[j + 0], sc.x, sh.x);
+        o[1] = fmaf(v[j + 1], sc.y, sh.y);
+        o[2] = fmaf(v[j + 2], sc.z, sh.z);
+        o[3] = fmaf(v[j + 3], sc.w, sh.w);
+        if (g.relu) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) o[u] = fmaxf(o[u], 0.f);
         }
         if (col0 + j + 3 < g.N) {
           if (rrow) {
