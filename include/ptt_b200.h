@@ -130,7 +130,7 @@ PTT_API size_t ptt_sa_params_floats(int C, int n_layers, const int* h_dims);
 PTT_API int ptt_sa_pack_params(int C, int n_layers, const int* h_dims, const float* const* h_weights,
                        const float* const* h_scale, const float* const* h_shift, float* params,
                        ptt_stream_t stream);
-PTT_API size_t ptt_sa_mlp_workspace_bytes(int B, int M, int ns, int C, int n_layers, const int* h_dims);
+PTT_API size_t ptt_sa_mlp_workspace_bytes(int B, int N, int M, int ns, int C, int n_layers, const int* h_dims);
 PTT_API int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, const float* new_xyz, const int* idx,
                    int B, int N, int M, int ns, int C, float radius, int normalize_xyz, int n_layers,
                    const int* h_dims, const float* params, float* out_pm, int ld_out, float* out_cm,

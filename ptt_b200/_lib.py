@@ -35,7 +35,7 @@ SIGNATURES = {
     "ptt_pm_to_cm": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "ptt_sa_params_floats": (c_size_t, [c_int, c_int, _IP]),
     "ptt_sa_pack_params": (c_int, [c_int, c_int, _IP, _PP, _PP, _PP, _P, _P]),
-    "ptt_sa_mlp_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, _IP]),
+    "ptt_sa_mlp_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, _IP]),
     "ptt_sa_mlp_fwd": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                _IP, _P, _P, c_int, _P, _P, c_size_t, _P]),
     "ptt_knn": (c_int, [_P, c_int, c_int, c_int, _P, _P]),

@@ -32,7 +32,9 @@ int ptt_gemm_launch_ffma(const PttGemmArgs& a, cudaStream_t st);
 // tcgen05 path (tc_gemm.cu)
 size_t ptt_tc_weight_halves(int K, int Cout);   // size of the fp16 image, in 2-byte units (multiple of 8192)
 // src(c, k) = w[c * ld_c + k * ld_k]: (Cout, K) row-major weight -> ld_c = K, ld_k = 1; transposed (K, ldw) image -> ld_c = 1, ld_k = ldw
-int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout, int K, void* img, cudaStream_t st);
+// row_scale (optional, Cout floats): the image holds diag(row_scale) . W
+int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout, int K, void* img, cudaStream_t st,
+                       const float* row_scale = nullptr);
 bool ptt_tc_gemm_supported(const PttGemmArgs& a);
 int ptt_tc_gemm_launch(const PttGemmArgs& a, const void* wimg, cudaStream_t st);
 // floats occupied by the tcgen05 image of a (Cout, K) weight

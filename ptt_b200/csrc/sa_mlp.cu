@@ -10,6 +10,7 @@
 // the layers run through the row-block contraction of gemm.cuh, a final kernel takes the max over
 // each centre's nsample rows and writes point-major and/or channel-major output.
 #include "gemm.cuh"
+#include "sa_fused.cuh"
 
 namespace {
 
@@ -20,6 +21,9 @@ struct SaLayout {
   int dims[SA_MAX_LAYERS + 1];
   int ldw[SA_MAX_LAYERS];
   size_t wt[SA_MAX_LAYERS], scale[SA_MAX_LAYERS], shift[SA_MAX_LAYERS], wimg[SA_MAX_LAYERS];
+  // fused path (sa_fused.cu), present when fused_dims: per-point layer-1 image, scaled xyz columns, scale-folded W2 / W3
+  bool fused_dims;
+  size_t g1img, wxs, w2s, w3s;
   size_t total;
 };
 
@@ -43,8 +47,25 @@ bool sa_layout(int C, int n_layers, const int* h_dims, SaLayout* L) {
     L->wimg[l] = off;      // fp16 hi/lo tensor-core image of the same (permuted) weight
     off += ptt_tc_weight_floats(L->dims[l], L->dims[l + 1]);
   }
+  L->fused_dims = n_layers == 3 && sa_fused_supported(L->dims[1], L->dims[2], L->dims[3], 32);
+  L->g1img = L->wxs = L->w2s = L->w3s = 0;
+  if (L->fused_dims) {
+    L->g1img = off; off += C > 0 ? ptt_tc_weight_floats(C, L->dims[1]) : 0;
+    L->wxs = off;   off += (size_t)3 * L->dims[1];
+    L->w2s = off;   off += ptt_tc_weight_floats(L->dims[1], L->dims[2]);
+    L->w3s = off;   off += ptt_tc_weight_floats(L->dims[2], L->dims[3]);
+  }
   L->total = off;
   return true;
+}
+
+// wxs[d, c] = scale1[c] * wt0[(C + d), c]     (the xyz rows of the permuted layer-0 image)
+__global__ void sa_pack_wx_kernel(const float* __restrict__ wt0, int ldw, int C, int d1, const float* __restrict__ scale,
+                                  float* __restrict__ wxs) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 3 * d1; e += gridDim.x * blockDim.x) {
+    const int d = e / d1, c = e - d * d1;
+    wxs[e] = scale[c] * wt0[(size_t)(C + d) * ldw + c];
+  }
 }
 
 // conv weight (Cout, Cin) with Cin ordered [xyz(3) | feats(C)]  ->  wt (Cin x ldw) with rows ordered
@@ -133,21 +154,39 @@ extern "C" int ptt_sa_pack_params(int C, int n_layers, const int* h_dims, const 
     int rc = ptt_tc_pack_weight(params + L.wt[l], 1, L.ldw[l], L.dims[l + 1], L.dims[l], params + L.wimg[l], st);
     if (rc != PTT_OK) return rc;
   }
+  if (L.fused_dims) {
+    int rc;
+    if (C > 0 && (rc = ptt_tc_pack_weight(params + L.wt[0], 1, L.ldw[0], L.dims[1], C, params + L.g1img, st))) return rc;
+    sa_pack_wx_kernel<<<ceil_div(3 * L.dims[1], 256), 256, 0, st>>>(params + L.wt[0], L.ldw[0], C, L.dims[1],
+                                                                    params + L.scale[0], params + L.wxs); PTT_LAUNCHED();
+    if ((rc = ptt_tc_pack_weight(params + L.wt[1], 1, L.ldw[1], L.dims[2], L.dims[1], params + L.w2s, st, params + L.scale[1]))) return rc;
+    if ((rc = ptt_tc_pack_weight(params + L.wt[2], 1, L.ldw[2], L.dims[3], L.dims[2], params + L.w3s, st, params + L.scale[2]))) return rc;
+  }
   return ptt_launch_status();
 }
 
 namespace {
 struct SaWorkspace {
+  bool fused;
   int ldx, ldh;
-  size_t x_off, ha_off, hb_off, pm_off, total;  // in floats
+  size_t x_off, ha_off, hb_off, pm_off, g_off, total;  // in floats
 };
-bool sa_workspace(int B, int M, int ns, int C, const SaLayout& L, SaWorkspace* W) {
+bool sa_workspace(int B, int N, int M, int ns, int C, const SaLayout& L, SaWorkspace* W) {
   const size_t rows = (size_t)B * M * ns;
   int cmax = 0;
   for (int l = 1; l <= L.n_layers; ++l) cmax = max(cmax, L.dims[l]);
   W->ldx = round_up(C + 3, 4);
   W->ldh = round_up(cmax, 4);
+  W->fused = L.fused_dims && sa_fused_supported(L.dims[1], L.dims[2], L.dims[3], ns);
   size_t off = 0;
+  if (W->fused) {
+    W->x_off = W->ha_off = W->hb_off = 0;
+    W->g_off = off;  off += align_up(C > 0 ? (size_t)B * N * L.dims[1] : 0, 64);
+    W->pm_off = off; off += align_up((size_t)B * M * W->ldh, 64);
+    W->total = off + 64;
+    return true;
+  }
+  W->g_off = 0;
   W->x_off = off;  off += align_up(rows * W->ldx, 64);
   W->ha_off = off; off += align_up(rows * W->ldh, 64);
   W->hb_off = off; off += align_up(rows * W->ldh, 64);
@@ -157,11 +196,11 @@ bool sa_workspace(int B, int M, int ns, int C, const SaLayout& L, SaWorkspace* W
 }
 }  // namespace
 
-extern "C" size_t ptt_sa_mlp_workspace_bytes(int B, int M, int ns, int C, int n_layers, const int* h_dims) {
+extern "C" size_t ptt_sa_mlp_workspace_bytes(int B, int N, int M, int ns, int C, int n_layers, const int* h_dims) {
   SaLayout L;
   SaWorkspace W;
-  if (B <= 0 || M <= 0 || ns <= 0 || !sa_layout(C, n_layers, h_dims, &L)) return 0;
-  sa_workspace(B, M, ns, C, L, &W);
+  if (B <= 0 || N <= 0 || M <= 0 || ns <= 0 || !sa_layout(C, n_layers, h_dims, &L)) return 0;
+  sa_workspace(B, N, M, ns, C, L, &W);
   return W.total * sizeof(float);
 }
 
@@ -177,11 +216,41 @@ extern "C" int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, con
   const int Cout = L.dims[n_layers];
   PTT_CHECK_ARG(out_pm == nullptr || ld_out >= Cout);
   SaWorkspace W;
-  sa_workspace(B, M, ns, C, L, &W);
+  sa_workspace(B, N, M, ns, C, L, &W);
   if (workspace == nullptr || workspace_bytes < W.total * sizeof(float)) return PTT_ERR_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(workspace) & 15u) != 0) return PTT_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   float* ws = static_cast<float*>(workspace);
+
+  if (W.fused && (out_pm == nullptr || (ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(out_pm) & 15u) == 0))) {
+    // ---- fused path: per-point layer-1 contraction, then ONE kernel for gather + layers 1-3 + max
+    int rc;
+    float* gprime = nullptr;
+    if (C > 0) {
+      gprime = ws + W.g_off;
+      PttGemmArgs g;
+      g.x = feats; g.ldx = ldf; g.R = B * N; g.K = C;
+      g.wt = params + L.wt[0]; g.ldw = L.ldw[0]; g.N = L.dims[1];
+      g.wimg = params + L.g1img;
+      g.scale = params + L.scale[0]; g.shift = params + L.shift[0]; g.relu = 0;
+      g.y = gprime; g.ldy = L.dims[1];
+      if ((rc = ptt_gemm_launch(g, st))) return rc;
+    }
+    float* pm = out_pm ? out_pm : ws + W.pm_off;
+    const int ld_pm = out_pm ? ld_out : W.ldh;
+    SaFusedArgs f;
+    f.xyz = xyz; f.new_xyz = new_xyz; f.idx = idx;
+    f.gprime = gprime; f.shift1 = params + L.shift[0]; f.wx = params + L.wxs;
+    f.w2img = params + L.w2s; f.w3img = params + L.w3s;
+    f.shift2 = params + L.shift[1]; f.shift3 = params + L.shift[2];
+    f.B = B; f.N = N; f.M = M; f.ns = ns; f.radius = radius; f.normalize = normalize_xyz;
+    f.out_pm = pm; f.ld_out = ld_pm; f.rows = (long long)B * M * ns;
+    if ((rc = sa_fused_launch(f, L.dims[1], L.dims[2], L.dims[3], st))) return rc;
+    if (out_cm) rc = ptt_pm_to_cm(pm, ld_pm, B, L.dims[3], M, out_cm, stream);
+    return rc;
+  }
+  if (W.fused) return PTT_ERR_INVALID_ARGUMENT;   // out_pm must be 16-byte aligned with ld_out % 4 == 0
+
   float* X = ws + W.x_off;
   float* H[2] = {ws + W.ha_off, ws + W.hb_off};
   const long long rows = (long long)B * M * ns;

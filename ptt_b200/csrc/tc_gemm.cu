@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 //   sw128_offset(r, c); rows >= Cout and k >= K are zero.
 //   src(c, k) = w[c * ld_c + k * ld_k]   (so a transposed (K, ldw) image can be the source too)
 __global__ void tc_pack_weight_kernel(const float* __restrict__ w, long long ld_c, long long ld_k, int Cout, int K, int NB,
-                                      int KB, __half* __restrict__ img) {
+                                      int KB, const float* __restrict__ row_scale, __half* __restrict__ img) {
   const long long total = (long long)NB * KB * 64 * 8;   // (block, row, chunk)
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(e & 7);
@@ -265,7 +265,8 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, long long ld_
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int k = kb * 64 + c * 8 + u;
-      const float x = (n < Cout && k < K) ? w[(long long)n * ld_c + (long long)k * ld_k] : 0.f;
+      float x = (n < Cout && k < K) ? w[(long long)n * ld_c + (long long)k * ld_k] : 0.f;
+      if (row_scale != nullptr && n < Cout) x *= row_scale[n];     // fold a per-output-channel scale into the weight
       tc::split_f16(x, hi[u], lo[u]);
     }
     uint8_t* base = reinterpret_cast<uint8_t*>(img) + (size_t)blk * 2 * W_BLOCK_BYTES + tc::sw128_offset(r, c);
@@ -295,11 +296,12 @@ size_t ptt_tc_weight_halves(int K, int Cout) {
   return (size_t)ceil_div(Cout, 64) * ceil_div(K, 64) * 2 * (W_BLOCK_BYTES / 2);
 }
 
-int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout, int K, void* img, cudaStream_t st) {
+int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout, int K, void* img, cudaStream_t st,
+                       const float* row_scale) {
   const int NB = ceil_div(Cout, 64), KB = ceil_div(K, 64);
   const long long total = (long long)NB * KB * 512;
   tc_pack_weight_kernel<<<(unsigned)llmin_((total + 255) / 256, 2048), 256, 0, st>>>(w, ld_c, ld_k, Cout, K, NB, KB,
-                                                                                      static_cast<__half*>(img)); PTT_LAUNCHED();
+                                                                                      row_scale, static_cast<__half*>(img)); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 

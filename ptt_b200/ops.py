@@ -296,8 +296,8 @@ class PackedSAMlp:
             torch.cuda.current_stream().synchronize()   # ws/scales/shifts temporaries may die after return
         self.cout = dims[-1]
 
-    def workspace_bytes(self, B, M, ns):
-        return _lib.lib().ptt_sa_mlp_workspace_bytes(B, M, ns, self.C, self.n_layers, self.h_dims)
+    def workspace_bytes(self, B, N, M, ns):
+        return _lib.lib().ptt_sa_mlp_workspace_bytes(B, N, M, ns, self.C, self.n_layers, self.h_dims)
 
 
 def sa_mlp_fwd(packed, xyz, feats_pm, new_xyz, idx, radius, normalize_xyz, want_pm=True, want_cm=True, workspace=None):
@@ -316,7 +316,7 @@ def sa_mlp_fwd(packed, xyz, feats_pm, new_xyz, idx, radius, normalize_xyz, want_
     with _DeviceGuard(dev):
         out_pm = torch.empty(B, M, packed.cout, dtype=_F, device=dev) if want_pm else None
         out_cm = torch.empty(B, packed.cout, M, dtype=_F, device=dev) if want_cm else None
-        ws_bytes = packed.workspace_bytes(B, M, ns)
+        ws_bytes = packed.workspace_bytes(B, N, M, ns)
         ws = workspace if workspace is not None else _workspace(ws_bytes, dev)
         check(L.ptt_sa_mlp_fwd(_ptr(xyz), _ptr(feats_pm) if packed.C > 0 else None, ldf, _ptr(new_xyz), _ptr(idx), B, N, M,
                                ns, packed.C, float(radius), int(bool(normalize_xyz)), packed.n_layers, packed.h_dims,

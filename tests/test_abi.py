@@ -63,7 +63,7 @@ def test_workspace_queries_are_host_only(built_lib):
     dims = (ctypes.c_int * 4)(131, 128, 128, 256)
     assert L.ptt_sa_params_floats(128, 3, dims) > 131 * 128 + 128 * 128 + 128 * 256
     assert L.ptt_sa_params_floats(127, 3, dims) == 0           # dims[0] must be C + 3
-    assert L.ptt_sa_mlp_workspace_bytes(2, 256, 32, 128, 3, dims) > 0
+    assert L.ptt_sa_mlp_workspace_bytes(2, 512, 256, 32, 128, 3, dims) > 0
     assert L.ptt_transformer_params_floats(256, 512) >= 1839360
     assert L.ptt_transformer_block_workspace_bytes(2, 128, 16, 256, 512) > 0
 

@@ -77,7 +77,10 @@ def test_transformer_with_exact_ties_matches_port():
 
 def test_sa_layer_random_shapes_vs_port():
     cases = [(300, 7, [7, 16, 32], 100, 0.5, 12, "fps"), (64, 0, [0, 8], 64, 0.9, 3, "fps"),
-             (512, 64, [64, 64, 64, 64, 96], 128, 0.4, 32, "sequence")]
+             (512, 64, [64, 64, 64, 64, 96], 128, 0.4, 32, "sequence"),
+             # shapes the fused tcgen05 kernel takes: ns in {8, 16}, partial last tile, with and without features
+             (200, 10, [10, 64, 64, 128], 50, 0.5, 16, "fps"), (100, 0, [0, 128, 128, 256], 33, 0.6, 8, "fps"),
+             (256, 128, [128, 128, 128, 256], 77, 0.5, 32, "fps"), (300, 0, [0, 64, 64, 128], 300, 0.3, 4, "fps")]
     for i, (n, cin, mlp, npoint, radius, ns, method) in enumerate(cases):
         sd = filled(sa_state_dict(mlp), 90 + i)
         xyz = synth.make_clouds(2, n, 91 + i, "sparse" if i == 0 else "dense")
