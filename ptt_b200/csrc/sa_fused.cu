@@ -11,18 +11,19 @@
 // element), and runs layers 2 and 3 on the tensor cores with the fp16 hi/lo split of tc_gemm.cu (3 MMAs per K-step).
 //
 // One CTA per SM, 128 pair-rows (128/ns centres) per tile, static round-robin over tiles.  Warp roles:
-//   warps 0-3  epilogue: D2 (TMEM) -> +shift, ReLU -> fp16 hi/lo -> HB (smem, UMMA K-major SW128);
-//                        D3 (TMEM) -> +shift, ReLU -> max over each centre's ns rows (redux.sync) -> out (B, M, D3)
-//   warps 4-7  producers: per-row (point index, rel xyz) -> gather G' -> layer 1 -> fp16 hi/lo -> HA (smem)
-//   warp  8    weight loader: W2 / W3 as 16 KB (64 out-channels x 64 k, hi+lo) blocks through a 5-stage ring (TMA engine)
-//   warp  9    TMEM allocation + the single thread issuing tcgen05.mma / tcgen05.commit
+//   warps 0-7   epilogue (warp w: TMEM lane quarter w%4, column half w/4):
+//                 D2 (TMEM) -> +shift, ReLU -> fp16 hi/lo -> HB (smem, UMMA K-major SW128);
+//                 D3 (TMEM) -> +shift, ReLU -> max over each centre's ns rows (redux.sync) -> out (B, M, D3)
+//   warps 8-15  producers: per-row (point index, rel xyz) -> gather G' -> layer 1 -> fp16 hi/lo -> HA (smem)
+//   warp  16    weight loader: W2 / W3 as 16 KB (64 out-channels x 64 k, hi+lo) blocks through a 5-stage ring (TMA engine)
+//   warp  17    TMEM allocation + the single thread issuing tcgen05.mma / tcgen05.commit
 // BatchNorm scales of layers 2 and 3 are folded into the packed weights, so both epilogues are acc + shift.
 #include "sa_fused.cuh"
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int SF_THREADS = 320;
+constexpr int SF_THREADS = 576;            // 8 epilogue + 8 producer warps + loader + MMA
 constexpr int SF_TM = 128;
 constexpr int SF_NS = 5;                       // ring stages
 constexpr uint32_t SF_ITEM_BYTES = 16384;      // one weight block: 64 rows x 64 k, hi (8 KB) + lo (8 KB)
@@ -39,7 +40,7 @@ struct SfCfg {
   static constexpr uint32_t D2_COL = 0, D3_COL = 128, TMEM_COLS = 512;
 };
 
-__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
@@ -48,8 +49,8 @@ __device__ __forceinline__ uint32_t pack2(__half a, __half b) {
 template <int D1, int D2, int D3>
 __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_constant__ SaFusedArgs a, const int num_tiles) {
   using Cfg = SfCfg<D1, D2, D3>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   uint8_t* HA = smem;
   uint8_t* HB = HA + Cfg::HA_BYTES;
   uint8_t* ring = HB + Cfg::HB_BYTES;
@@ -75,24 +76,25 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       tc::mbar_init(&full_b[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
-    tc::mbar_init(ha_full, 128);
+    tc::mbar_init(ha_full, 256);
     tc::mbar_init(ha_free, 1);
     tc::mbar_init(d2_full, 1);
-    tc::mbar_init(hb_full, 128);
+    tc::mbar_init(hb_full, 256);
     tc::mbar_init(d3_full, 1);
     tc::mbar_init_fence();
   }
-  if (warp == 9) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 17) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int ns = a.ns;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =================================================================== epilogue warps
-    const int r = warp * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const unsigned gmask = ns >= 32 ? 0xffffffffu : (((1u << ns) - 1u) << (lane & ~(ns - 1)));
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       tc::mbar_wait(d2_full, par);
       tc::tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < D2; c0 += 32) {
+      for (int c0 = half * 32; c0 < D2; c0 += 64) {
         float v[32];
         tc::tmem_ld32(lane_addr + Cfg::D2_COL + (uint32_t)c0, v);
         uint8_t* blk = HB + (c0 >> 6) * SF_KBLOCK_BYTES;
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       const bool writer = (lane & (ns - 1)) == 0 && R < a.rows;
       float* orow = a.out_pm + (R / ns) * (long long)a.ld_out;
 #pragma unroll 1
-      for (int c0 = 0; c0 < D3; c0 += 32) {
+      for (int c0 = half * 32; c0 < D3; c0 += 64) {
         float v[32];
         tc::tmem_ld32(lane_addr + Cfg::D3_COL + (uint32_t)c0, v);
 #pragma unroll
@@ -147,11 +149,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       }
       tc::tc_fence_before();
     }
-  } else if (warp < 8) {
+  } else if (warp < 16) {
     // =================================================================== producers: layer 1 on CUDA cores
-    const int pt = tid - 128;            // 0..127
+    const int pt = tid - 256;            // 0..255
     const int q = pt & 15;               // float4 column (and q + 16 when D1 == 128)
-    const int rsub = pt >> 4;            // 0..7
+    const int rsub = pt >> 4;            // 0..15
     constexpr int NQ = D1 / 64;          // float4 columns per thread
     float wx[NQ][3][4], g0[NQ][4];
 #pragma unroll
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       // per-row neighbour info
       producer_bar();                                   // everyone is done reading s_info of the previous tile
-      {
+      if (pt < SF_TM) {
         const long long R = (long long)tile * SF_TM + pt;
         float4 info = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         if (R < a.rows) {
@@ -185,8 +187,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       producer_bar();
       tc::mbar_wait(ha_free, (uint32_t)(it & 1) ^ 1u);  // GEMM2 of the previous tile has consumed HA
 #pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int r = i * 8 + rsub;
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 16 + rsub;
         const float4 info = s_info[r];
         const int src = __float_as_int(info.w);
 #pragma unroll
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(ha_full);
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // =================================================================== weight loader
     if (lane == 0) {
       int stage = 0;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 17) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }

@@ -45,8 +45,8 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   uint8_t* ctrl = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* full_a = reinterpret_cast<uint64_t*>(ctrl);           // [STAGES]
   uint64_t* full_b = full_a + STAGES;                              // [STAGES]

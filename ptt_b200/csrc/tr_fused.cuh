@@ -1,0 +1,36 @@
+// Internal interface of the transformer pair-row passes (tr_fused.cu); see that file for the design.
+#pragma once
+
+#include "common.cuh"
+
+enum TrProducer { TR_PROD_PLAIN = 0, TR_PROD_DELTA0 = 1, TR_PROD_QKPOS = 2 };
+enum TrEpilogue { TR_EPI_STORE = 0, TR_EPI_SOFTMAX = 1 };
+
+struct TrPassArgs {
+  int n = 0, k = 0, dm = 0;      // tokens per cloud, neighbours per token, d_model
+  long long pairs = 0;           // B * n * k rows
+  const float* xyz = nullptr;    // (B, n, 3)
+  const int* knn = nullptr;      // (B, n, k) neighbour index inside the cloud
+  // producer sources
+  const float* a_src = nullptr;  // PLAIN: (pairs, lda) fp32 rows
+  int lda = 0;
+  const float* wd0 = nullptr;    // DELTA0: fc_delta.0 image, rows 0..2 = weight^T (3, ldw0), row 3 = bias
+  int ldw0 = 0;
+  const float* qkv = nullptr;    // QKPOS producer / SOFTMAX epilogue: (B*n, ldq) with q at column 0, k at koff, v at voff
+  int ldq = 0, koff = 0, voff = 0;
+  const float* pos = nullptr;    // (pairs, dm): QKPOS producer input, SOFTMAX epilogue input
+  // contraction
+  const void* wimg = nullptr;    // tcgen05 image of the (dm, dm) weight
+  const float* bias = nullptr;   // (dm)
+  int relu = 0;
+  // outputs
+  float* out = nullptr;          // STORE: (pairs, ldo);  SOFTMAX: res (B*n, ldo)
+  int ldo = 0;
+  float* attn = nullptr;         // SOFTMAX, optional: (pairs, dm) softmax weights
+  float divisor = 1.f;           // sqrt(d_model)
+  const float* x_sub = nullptr;  // SOFTMAX, Offset variant: res = x_sub - res   (B*n, ldx)
+  int ldx = 0;
+};
+
+bool tr_fused_supported(int n, int k, int dm);
+int tr_fused_launch(const TrPassArgs& a, int producer, int epilogue, cudaStream_t st);

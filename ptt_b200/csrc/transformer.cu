@@ -11,6 +11,7 @@
 // through gemm.cuh, the gathers / softmax / weighted sum in fused element kernels.  The (B,n,n)
 // distance matrix, its argsort and the three (B,n,k,d) gathered tensors of the reference are never built.
 #include "gemm.cuh"
+#include "tr_fused.cuh"
 
 namespace {
 
@@ -233,6 +234,31 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
 
   if ((rc = linear(features, dp, tokens, dp, L.fc1, dm, ld, true, 0, nullptr, 0, x, ld))) return rc;
   if ((rc = linear(x, ld, tokens, dm, L.qkv, 3 * ld, 3 * ld, false, 0, nullptr, 0, qkv, ldq))) return rc;
+
+  if (tr_fused_supported(n, k, dm)) {
+    // ---- pair-row passes on the tensor cores with generated A operands and fused reductions (tr_fused.cu)
+    auto img_w = [&](size_t img) { return params + img + (size_t)(dm + 1) * ld; };   // tcgen05 image behind the fp32 one
+    auto img_b = [&](size_t img) { return params + img + (size_t)dm * ld; };         // bias row
+    TrPassArgs t;
+    t.n = n; t.k = k; t.dm = dm; t.pairs = pairs; t.xyz = xyz; t.knn = knn;
+    t.qkv = qkv; t.ldq = ldq; t.koff = ld; t.voff = 2 * ld; t.divisor = sqrtf((float)dm);
+    // pass 1: pos = fc_delta.2(relu(fc_delta.0(xyz_i - xyz_j)))
+    TrPassArgs p1 = t;
+    p1.wd0 = params + L.delta0; p1.ldw0 = ld;
+    p1.wimg = img_w(L.delta2); p1.bias = img_b(L.delta2); p1.relu = 0; p1.out = pos; p1.ldo = ld;
+    if ((rc = tr_fused_launch(p1, TR_PROD_DELTA0, TR_EPI_STORE, st))) return rc;
+    // pass 2: g = relu(fc_gamma.0(q_i - k_j + pos))
+    TrPassArgs p2 = t;
+    p2.pos = pos; p2.wimg = img_w(L.gamma0); p2.bias = img_b(L.gamma0); p2.relu = 1; p2.out = h; p2.ldo = ld;
+    if ((rc = tr_fused_launch(p2, TR_PROD_QKPOS, TR_EPI_STORE, st))) return rc;
+    // pass 3: logits = fc_gamma.2(g); softmax over the k neighbours; res = sum p * (v + pos)
+    TrPassArgs p3 = t;
+    p3.a_src = h; p3.lda = ld; p3.pos = pos; p3.wimg = img_w(L.gamma2); p3.bias = img_b(L.gamma2);
+    p3.out = res; p3.ldo = ld; p3.attn = attn_or_null;
+    if (variant == 1) { p3.x_sub = x; p3.ldx = ld; }
+    if ((rc = tr_fused_launch(p3, TR_PROD_PLAIN, TR_EPI_SOFTMAX, st))) return rc;
+    return linear(res, ld, tokens, dm, L.fc2, dp, round_up(dp, 4), true, 0, features, dp, out, dp);
+  }
   tr_delta0_kernel<<<grid_for(pairs * dm), 256, 0, st>>>(xyz, knn, params + L.delta0, n, k, dm, ld, pairs, h, ld); PTT_LAUNCHED();
   if ((rc = linear(h, ld, pairs, dm, L.delta2, dm, ld, true, 0, nullptr, 0, pos, ld))) return rc;
   tr_attn_in_kernel<<<grid_for(pairs * dm), 256, 0, st>>>(qkv, ldq, ld, knn, pos, n, k, dm, pairs, a, ld); PTT_LAUNCHED();

@@ -64,7 +64,16 @@ class HotPath:
         self.box_sa = pack_sa_module(_sub(sd, "box_voting_head.vote_aggregation."), eps)
         self.box_tr = ops.PackedTransformer(_sub(sd, "box_voting_head.transformer_block."), self.cfg["knn"])
         self.streams = None
+        self._ws = {}                 # persistent per-stage workspaces (no allocator traffic in steady state)
         self.stage_events = None      # set to {} to record (start, end) CUDA events per stage on its stream
+
+    def _workspace(self, tag, nbytes):
+        need = max(int(nbytes), 16) // 4 + 4
+        ws = self._ws.get(tag)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.float32, device=self.device)
+            self._ws[tag] = ws
+        return ws
 
     def profile(self, on=True):
         self.stage_events = {} if on else None
@@ -102,9 +111,10 @@ class HotPath:
             raise NotImplementedError(method)
         with self._Stage(self, tag + ".ball_query"):
             idx = ops.ball_query(new_xyz, xyz, radius, nsample)
+        ws = self._workspace(tag, packed.workspace_bytes(xyz.shape[0], xyz.shape[1], npoint, nsample))
         with self._Stage(self, tag + ".mlp"):
             out_pm, out_cm = ops.sa_mlp_fwd(packed, xyz, feats_pm, new_xyz, idx, radius, c["normalize_xyz"],
-                                            want_pm=True, want_cm=want_cm)
+                                            want_pm=True, want_cm=want_cm, workspace=ws)
         return new_xyz, out_pm, out_cm, inds
 
     # a8: PointNet2BackboneLight.branch_forward (pointnet2_backbone.py:41-50)
@@ -147,13 +157,15 @@ class HotPath:
         with torch.cuda.stream(s1):
             s_xyz, s_feat_pm, s_inds = self.backbone_branch(search, c["npoints_search"])
             s_feat = ops.pm_to_cm(s_feat_pm)
+            ws = self._workspace("centroid.transformer", self.centroid_tr.workspace_bytes(s_xyz.shape[0], s_xyz.shape[1]))
             with self._Stage(self, "centroid.transformer"):
-                cen = ops.transformer_block_fwd(self.centroid_tr, s_xyz, s_feat_pm)
+                cen = ops.transformer_block_fwd(self.centroid_tr, s_xyz, s_feat_pm, workspace=ws)
             votes_pm = torch.cat([torch.full_like(cen[:, :, :1], 0.5), cen], dim=2)     # glue: [score | feats]
             b_xyz, b_feat_pm, b_feat, _ = self._sa_layer(self.box_sa, s_xyz, votes_pm, c["box_npoint"], c["box_radius"],
                                                          c["box_nsample"], "fps", want_cm=True, tag="box.sa")
+            ws = self._workspace("box.transformer", self.box_tr.workspace_bytes(b_xyz.shape[0], b_xyz.shape[1]))
             with self._Stage(self, "box.transformer"):
-                box = ops.transformer_block_fwd(self.box_tr, b_xyz, b_feat_pm)
+                box = ops.transformer_block_fwd(self.box_tr, b_xyz, b_feat_pm, workspace=ws)
         cur.wait_stream(s1)
         cur.wait_stream(s2)
         for t in (t_xyz, t_feat_pm, t_feat, t_inds, s_xyz, s_feat_pm, s_feat, s_inds, cen, votes_pm, b_xyz, b_feat_pm,
