@@ -194,3 +194,28 @@ def test_hot_path_full_batch_properties():
         assert np.array_equal(sub[k].cpu().numpy(), want[k].numpy()), k
     for k in ("search_feats", "template_feats", "centroid_feats", "box_sa_feats", "box_feats"):
         np.testing.assert_allclose(sub[k].cpu().numpy(), want[k].numpy(), err_msg=k, **FP_TOL)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("shape", [(3, 128, 256, 512, 16), (5, 64, 64, 128, 8), (2, 100, 32, 256, 4), (1, 32, 128, 64, 32)])
+def test_transformer_cluster_sizes_agree_with_port(cluster, shape):
+    """Every thread-block-cluster size of the tcgen05 transformer passes (weights multicast to 1, 2 or 4 CTAs),
+    including tile counts that are not a multiple of the cluster size (dummy tiles), against the CPU port."""
+    import ctypes
+    from ptt_b200 import _lib
+    B, n, dp, dm, k = shape
+    sd = filled(transformer_state_dict("TransformerBlock", dp, dm), 300 + n)
+    xyz = synth.make_clouds(B, n, 301 + n, "dense", role="template")
+    f = synth.features((B, n, dp), seed=302 + n)
+    want, want_attn = torch_port.transformer_block(sd, t(xyz), t(f), k)
+    packed = ops.PackedTransformer({kk: g(v) for kk, v in sd.items()}, k)
+    setter = _lib.lib().ptt_debug_set_cluster
+    setter.argtypes = [ctypes.c_int]
+    setter(cluster)
+    try:
+        got, attn = ops.transformer_block_fwd(packed, g(xyz), g(f), want_attn=True)
+        torch.cuda.synchronize()
+    finally:
+        setter(0)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), **FP_TOL)
+    np.testing.assert_allclose(attn.cpu().numpy(), want_attn.numpy(), **FP_TOL)
