@@ -28,6 +28,7 @@ struct TrPassArgs {
   int ldo = 0;
   float* attn = nullptr;         // SOFTMAX, optional: (pairs, dm) softmax weights
   float divisor = 1.f;           // sqrt(d_model)
+  long long* dbg = nullptr;      // optional timeline buffer (clock64 stamps of CTA 0; tuning only)
   const float* x_sub = nullptr;  // SOFTMAX, Offset variant: res = x_sub - res   (B*n, ldx)
   int ldx = 0;
 };

@@ -219,3 +219,22 @@ def test_transformer_cluster_sizes_agree_with_port(cluster, shape):
         setter(0)
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), **FP_TOL)
     np.testing.assert_allclose(attn.cpu().numpy(), want_attn.numpy(), **FP_TOL)
+
+
+def test_hot_path_graph_replay_matches_eager_and_host_api():
+    sd = synth.hot_path_state_dict(0)
+    hp = hotpath.HotPath(sd, device=DEV)
+    outs = []
+    for seed in (600, 601, 602):
+        search = g(synth.make_clouds(4, 1024, seed, "dense"))
+        template = g(synth.make_clouds(4, 512, seed + 50, "dense", role="template"))
+        eager = {k: v.clone() for k, v in hp(search, template).items()}
+        replay = {k: v.clone() for k, v in hp.forward_graph(search, template).items()}
+        torch.cuda.synchronize()
+        for k in eager:
+            assert torch.equal(eager[k], replay[k]), k          # same kernels, same order: bit-identical
+        host = hp.forward_host(search.cpu().pin_memory(), template.cpu().pin_memory())
+        for k in eager:
+            assert torch.equal(eager[k].cpu(), host[k]), k
+        outs.append(eager["box_feats"])
+    assert not torch.equal(outs[0], outs[1])

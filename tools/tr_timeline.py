@@ -1,0 +1,47 @@
+"""Tuning aid: clock64 timeline of CTA 0 of one transformer pair-row pass (pass 1: generated A, store epilogue)."""
+import ctypes, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from ptt_b200 import _lib, ops, synth
+
+cs = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+B, n, k, dm = 48, 128, 16, 512
+L = _lib.lib()
+L.ptt_debug_set_cluster.argtypes = [ctypes.c_int]
+L.ptt_debug_set_cluster(cs)
+fn = L.ptt_debug_tr_pass_timeline
+fn.restype = ctypes.c_int
+fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+xyz = torch.from_numpy(synth.make_clouds(B, n, 1, "dense", role="template")).cuda()
+knn = ops.knn(xyz, k)
+w = torch.randn(dm, dm, device="cuda") / dm ** 0.5
+b = torch.randn(dm, device="cuda")
+lin = ops.PackedLinear(w, b)
+wd0 = torch.randn(4, dm, device="cuda")
+out = torch.empty(B * n * k, dm, device="cuda")
+dbg = torch.zeros(2000, dtype=torch.int64, device="cuda")
+ldw = dm
+wimg_ptr = lin.params.data_ptr() + (dm + 1) * ldw * 4
+for rep in range(3):
+    dbg.zero_()
+    rc = fn(xyz.data_ptr(), knn.data_ptr(), B, n, k, dm, wd0.data_ptr(), dm, wimg_ptr, b.data_ptr(), out.data_ptr(), dbg.data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rc == 0, rc
+d = dbg.cpu().numpy()
+t0 = None
+ev = []
+for i in range(400):
+    tag, t = int(d[2 * i]), int(d[2 * i + 1])
+    if tag == -1 or (tag == 0 and t == 0):
+        break
+    if t0 is None:
+        t0 = t
+    ev.append((tag, t - t0))
+print("cluster", cs, "events", len(ev))
+prev = 0
+for tag, t in ev:
+    print("%4d %8d  (+%d)" % (tag, t, t - prev))
+    prev = t
+print("epilogue d_full / d_free stamps (rel):", [(int(d[1000 + 2 * i]) - t0, int(d[1001 + 2 * i]) - t0) for i in range(6)])
