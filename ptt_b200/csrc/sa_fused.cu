@@ -241,8 +241,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       }
     }
   } else {
-    // =================================================================== MMA issuer
-    if (lane == 0) {
+    // =================================================================== MMA issuer (whole warp, one elected lane issues)
+    {
       constexpr uint32_t IDESC = tc::idesc_f16<false>(SF_TM, 64);
       int stage = 0;
       uint32_t phase = 0;
@@ -267,16 +267,16 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);
-              tc::mma_f16(d, da_hi + adv, db_hi + adv, IDESC, (kb | k) != 0);
-              tc::mma_f16(d, da_lo + adv, db_hi + adv, IDESC, 1);
-              tc::mma_f16(d, da_hi + adv, db_lo + adv, IDESC, 1);
+              tc::mma_f16_w(d, da_hi + adv, db_hi + adv, IDESC, (kb | k) != 0);
+              tc::mma_f16_w(d, da_lo + adv, db_hi + adv, IDESC, 1);
+              tc::mma_f16_w(d, da_hi + adv, db_lo + adv, IDESC, 1);
             }
-            tc::mma_commit(&empty[stage]);
+            tc::mma_commit_w(&empty[stage]);
             if (++stage == SF_NS) { stage = 0; phase ^= 1; }
           }
         }
-        tc::mma_commit(ha_free);
-        tc::mma_commit(d2_full);
+        tc::mma_commit_w(ha_free);
+        tc::mma_commit_w(d2_full);
         // ---- layer 3: D3 = H2 . W3'^T
         tc::mbar_wait(hb_full, par);
         tc::tc_fence_after();
@@ -294,15 +294,15 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);
-              tc::mma_f16(d, da_hi + adv, db_hi + adv, IDESC, (kb | k) != 0);
-              tc::mma_f16(d, da_lo + adv, db_hi + adv, IDESC, 1);
-              tc::mma_f16(d, da_hi + adv, db_lo + adv, IDESC, 1);
+              tc::mma_f16_w(d, da_hi + adv, db_hi + adv, IDESC, (kb | k) != 0);
+              tc::mma_f16_w(d, da_lo + adv, db_hi + adv, IDESC, 1);
+              tc::mma_f16_w(d, da_hi + adv, db_lo + adv, IDESC, 1);
             }
-            tc::mma_commit(&empty[stage]);
+            tc::mma_commit_w(&empty[stage]);
             if (++stage == SF_NS) { stage = 0; phase ^= 1; }
           }
         }
-        tc::mma_commit(d3_full);
+        tc::mma_commit_w(d3_full);
       }
     }
   }

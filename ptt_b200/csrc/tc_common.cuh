@@ -121,6 +121,35 @@ __device__ __forceinline__ void mma_commit_mcast(uint64_t* bar, uint16_t cta_mas
                : "memory");
 }
 
+// ---- warp-convergent issue: the WHOLE warp executes these and one elected lane issues.  Keeping the issuing warp
+// convergent lets the compiler hold descriptors / addresses in uniform registers (UTCHMMA takes uniform operands);
+// issuing from a divergent `if (lane == 0)` costs ~15 extra instructions (R2UR / ELECT / vote) per MMA.
+__device__ __forceinline__ void mma_f16_w(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mcast_w(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -137,6 +166,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 256-bit global store (sm_100+): one full 32-byte sector per lane (address 32-byte aligned)
+__device__ __forceinline__ void st_global_v8(float* p, const float (&o)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
+               "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+               : "memory");
 }
 
 // ---------------------------------------------------------------- descriptors

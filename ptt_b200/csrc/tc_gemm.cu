@@ -212,8 +212,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       }
     }
   } else {
-    // ------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+    {
       constexpr uint32_t IDESC = tc::idesc_f16<false>(TBM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -229,14 +229,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < TBK / 16; ++k) {
           const uint64_t adv = (uint64_t)(k * 2);   // 32 bytes per UMMA_K, in 16-byte units of the address field
-          tc::mma_f16(tmem_base, da_hi + adv, db_hi + adv, IDESC, (kb | k) != 0);
-          tc::mma_f16(tmem_base, da_lo + adv, db_hi + adv, IDESC, 1);
-          tc::mma_f16(tmem_base, da_hi + adv, db_lo + adv, IDESC, 1);
+          tc::mma_f16_w(tmem_base, da_hi + adv, db_hi + adv, IDESC, (kb | k) != 0);
+          tc::mma_f16_w(tmem_base, da_lo + adv, db_hi + adv, IDESC, 1);
+          tc::mma_f16_w(tmem_base, da_hi + adv, db_lo + adv, IDESC, 1);
         }
-        tc::mma_commit(&empty[stage]);     // frees the stage once these MMAs have read it
+        tc::mma_commit_w(&empty[stage]);     // frees the stage once these MMAs have read it
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      tc::mma_commit(accum_full);
+      tc::mma_commit_w(accum_full);
     }
   }
 

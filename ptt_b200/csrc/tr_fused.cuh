@@ -29,6 +29,7 @@ struct TrPassArgs {
   float* attn = nullptr;         // SOFTMAX, optional: (pairs, dm) softmax weights
   float divisor = 1.f;           // sqrt(d_model)
   long long* dbg = nullptr;      // optional timeline buffer (clock64 stamps of CTA 0; tuning only)
+  int dbg_flags = 0;             // tuning only: 1 = skip the epilogue's global stores, 2 = loader re-reads one weight item
   const float* x_sub = nullptr;  // SOFTMAX, Offset variant: res = x_sub - res   (B*n, ldx)
   int ldx = 0;
 };
