@@ -181,7 +181,7 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
 
-    from ptt_b200 import _lib, hotpath, synth
+    from ptt_b200 import _lib, hotpath, shard, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -266,10 +266,7 @@ def run_b200(a):
     h2d = search_h[0].numel() * 4 + templ_h[0].numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in out_h.values())
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3, t_wall * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_ms = [float(x) for x in times.tolist()]
+    dev_ms, e2e_ms, wall_ms = shard.max_over_ranks([dev_ms, e2e_s * 1e3, t_wall * 1e3], device=dev)   # slowest rank
 
     if rank == 0:
         frames = B * n_gpus * a.steps
@@ -284,7 +281,7 @@ def run_b200(a):
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         achieved_tf = alg[top] * B / (known[top] * 1e-3) / 1e12
         line = {
-            "metric": METRIC, "value": frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
+            "metric": METRIC, "value": shard.whole_job_throughput(B * a.steps, n_gpus, dev_ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, n_gpus),
             "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

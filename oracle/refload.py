@@ -36,8 +36,15 @@ def load():
         _ident._oracle_identity = True
         torch.Tensor.cuda = _ident
         torch.nn.Module.cuda = _ident
+    # another `pointnet2_ops` (e.g. the product drop-in, installed by a test in the same process) must not win here
+    for name in [m for m in sys.modules if m == "pointnet2_ops" or m.startswith("pointnet2_ops.")]:
+        if not getattr(sys.modules[name], "__file__", "").startswith(_SHIMS):
+            del sys.modules[name]
+    import pointnet2_ops._ext as shim_ext  # noqa: E402
     import ptt.models as models  # noqa: E402
+    import ptt.models.backbones_3d.pointnet2.pointnet2_utils as pu  # noqa: E402
 
+    pu._ext = shim_ext
     return models
 
 
