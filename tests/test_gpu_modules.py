@@ -196,7 +196,7 @@ def test_hot_path_full_batch_properties():
         np.testing.assert_allclose(sub[k].cpu().numpy(), want[k].numpy(), err_msg=k, **FP_TOL)
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("cluster", [1, 2, 4, -2])
 @pytest.mark.parametrize("shape", [(3, 128, 256, 512, 16), (5, 64, 64, 128, 8), (2, 100, 32, 256, 4), (1, 32, 128, 64, 32)])
 def test_transformer_cluster_sizes_agree_with_port(cluster, shape):
     """Every thread-block-cluster size of the tcgen05 transformer passes (weights multicast to 1, 2 or 4 CTAs),
