@@ -49,4 +49,5 @@ prev = 0
 for tag, t in ev:
     print("%4d %8d  (+%d)" % (tag, t, t - prev))
     prev = t
-print("epilogue d_full / d_free stamps (rel):", [(int(d[1000 + 2 * i]) - t0, int(d[1001 + 2 * i]) - t0) for i in range(6)])
+if t0 is not None:
+    print("epilogue d_full / d_free stamps (rel):", [(int(d[1000 + 2 * i]) - t0, int(d[1001 + 2 * i]) - t0) for i in range(6)])
