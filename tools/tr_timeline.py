@@ -21,7 +21,7 @@ b = torch.randn(dm, device="cuda")
 lin = ops.PackedLinear(w, b)
 wd0 = torch.randn(4, dm, device="cuda")
 out = torch.empty(B * n * k, dm, device="cuda")
-dbg = torch.zeros(2000, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(6000, dtype=torch.int64, device="cuda")
 ldw = dm
 wimg_ptr = lin.params.data_ptr() + (dm + 1) * ldw * 4
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -45,6 +45,12 @@ for i in range(400):
         t0 = t
     ev.append((tag, t - t0))
 print("cluster", cs, "events", len(ev))
+if t0 is not None:
+    print("producer thread 0: (kb: wait_start, wait_end, produced) rel cycles")
+    for i in range(24):
+        a0, a1, a2 = (int(d[2000 + i * 3 + j]) for j in range(3))
+        if a0:
+            print("  unit %d kb %d: %8d %8d %8d   wait %6d produce %6d" % (i // 8, i % 8, a0 - t0, a1 - t0, a2 - t0, a1 - a0, a2 - a1))
 prev = 0
 for tag, t in ev:
     print("%4d %8d  (+%d)" % (tag, t, t - prev))
