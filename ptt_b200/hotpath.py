@@ -215,6 +215,31 @@ class HotPath:
         graph.replay()
         return out
 
+    # ------------------------------------------------------------------------------------------------
+    # Asynchronous host API: submit() enqueues H2D + graph replay + D2H on this instance's own stream and returns at
+    # once; collect() waits for that step's results.  Two instances used alternately (HostPipeline) overlap the
+    # copies and the serial stretches (FPS, ball query) of one step with the dense kernels of the next.
+    # ------------------------------------------------------------------------------------------------
+    def submit_host(self, search_host, template_host):
+        if getattr(self, "_io_stream", None) is None:
+            self._io_stream = torch.cuda.Stream(self.device)
+            self._done = torch.cuda.Event()
+        with torch.cuda.stream(self._io_stream):
+            search = search_host.to(self.device, non_blocking=True)
+            template = template_host.to(self.device, non_blocking=True)
+            out = self.forward_graph(search, template)
+            bufs = getattr(self, "_host_out", None)
+            if bufs is None or any(tuple(bufs[k].shape) != tuple(out[k].shape) for k in self.HOST_KEYS):
+                bufs = {k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True) for k in self.HOST_KEYS}
+                self._host_out = bufs
+            for k in self.HOST_KEYS:
+                bufs[k].copy_(out[k], non_blocking=True)
+            self._done.record(self._io_stream)
+
+    def collect_host(self):
+        self._done.synchronize()
+        return self._host_out
+
     HOST_KEYS = ("search_seeds", "search_feats", "search_inds", "template_seeds", "template_feats", "template_inds",
                  "centroid_feats", "box_centers", "box_sa_feats", "box_feats")
 
@@ -234,3 +259,33 @@ class HotPath:
             bufs[k].copy_(out[k], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return bufs
+
+
+class HostPipeline:
+    """Throughput-oriented host API: `depth` HotPath instances (own CUDA graph, workspaces, streams, pinned output
+    buffers) used round-robin, so step i+1's H2D copy and compute overlap step i's D2H copy and serial stretches.
+
+        pipe = HostPipeline(state_dict)
+        for search, template in frames:            # pinned CPU tensors
+            prev = pipe.push(search, template)     # results of the step submitted depth-1 pushes ago (or None)
+        tail = pipe.drain()                        # remaining results, oldest first
+    """
+
+    def __init__(self, state_dict, cfg=None, device="cuda", depth=2):
+        self.slots = [HotPath(state_dict, cfg=cfg, device=device) for _ in range(depth)]
+        self.pending = []          # slot indices in submission order
+        self.next = 0
+
+    def push(self, search_host, template_host):
+        out = None
+        if len(self.pending) == len(self.slots):
+            out = self.slots[self.pending.pop(0)].collect_host()
+        self.slots[self.next].submit_host(search_host, template_host)
+        self.pending.append(self.next)
+        self.next = (self.next + 1) % len(self.slots)
+        return out
+
+    def drain(self):
+        outs = [self.slots[i].collect_host() for i in self.pending]
+        self.pending = []
+        return outs

@@ -238,3 +238,22 @@ def test_hot_path_graph_replay_matches_eager_and_host_api():
             assert torch.equal(eager[k].cpu(), host[k]), k
         outs.append(eager["box_feats"])
     assert not torch.equal(outs[0], outs[1])
+
+
+def test_host_pipeline_matches_synchronous_api():
+    sd = synth.hot_path_state_dict(0)
+    hp = hotpath.HotPath(sd, device=DEV)
+    pipe = hotpath.HostPipeline(sd, device=DEV, depth=2)
+    batches = [(t(synth.make_clouds(3, 1024, 700 + i, "dense")).pin_memory(),
+                t(synth.make_clouds(3, 512, 750 + i, "dense", role="template")).pin_memory()) for i in range(5)]
+    want = [{k: v.clone() for k, v in hp.forward_host(s, tm).items()} for s, tm in batches]
+    got = []
+    for s, tm in batches:
+        r = pipe.push(s, tm)
+        if r is not None:
+            got.append({k: v.clone() for k, v in r.items()})
+    got += [{k: v.clone() for k, v in r.items()} for r in pipe.drain()]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
