@@ -220,14 +220,22 @@ class HotPath:
     # once; collect() waits for that step's results.  Two instances used alternately (HostPipeline) overlap the
     # copies and the serial stretches (FPS, ball query) of one step with the dense kernels of the next.
     # ------------------------------------------------------------------------------------------------
-    def submit_host(self, search_host, template_host):
+    def submit_host(self, search_host, template_host, to_host=True, after=None):
+        """Inputs: pinned CPU tensors (copied H2D) or CUDA tensors.  to_host=False leaves the results on the device
+        (collect_host then returns the graph's static output tensors).  `after`: CUDA event to wait for first."""
         if getattr(self, "_io_stream", None) is None:
             self._io_stream = torch.cuda.Stream(self.device)
             self._done = torch.cuda.Event()
         with torch.cuda.stream(self._io_stream):
+            if after is not None:
+                self._io_stream.wait_event(after)
             search = search_host.to(self.device, non_blocking=True)
             template = template_host.to(self.device, non_blocking=True)
             out = self.forward_graph(search, template)
+            if not to_host:
+                self._dev_out = out
+                self._done.record(self._io_stream)
+                return
             bufs = getattr(self, "_host_out", None)
             if bufs is None or any(tuple(bufs[k].shape) != tuple(out[k].shape) for k in self.HOST_KEYS):
                 bufs = {k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True) for k in self.HOST_KEYS}
@@ -236,9 +244,9 @@ class HotPath:
                 bufs[k].copy_(out[k], non_blocking=True)
             self._done.record(self._io_stream)
 
-    def collect_host(self):
+    def collect_host(self, to_host=True):
         self._done.synchronize()
-        return self._host_out
+        return self._host_out if to_host else self._dev_out
 
     HOST_KEYS = ("search_seeds", "search_feats", "search_inds", "template_seeds", "template_feats", "template_inds",
                  "centroid_feats", "box_centers", "box_sa_feats", "box_feats")
@@ -276,16 +284,16 @@ class HostPipeline:
         self.pending = []          # slot indices in submission order
         self.next = 0
 
-    def push(self, search_host, template_host):
+    def push(self, search_host, template_host, to_host=True, after=None):
         out = None
         if len(self.pending) == len(self.slots):
-            out = self.slots[self.pending.pop(0)].collect_host()
-        self.slots[self.next].submit_host(search_host, template_host)
+            out = self.slots[self.pending.pop(0)].collect_host(to_host)
+        self.slots[self.next].submit_host(search_host, template_host, to_host=to_host, after=after)
         self.pending.append(self.next)
         self.next = (self.next + 1) % len(self.slots)
         return out
 
-    def drain(self):
-        outs = [self.slots[i].collect_host() for i in self.pending]
+    def drain(self, to_host=True):
+        outs = [self.slots[i].collect_host(to_host) for i in self.pending]
         self.pending = []
         return outs
