@@ -247,6 +247,7 @@ def run_b200(a):
 
     # ---- per-stage pass (roofline): the same K steps launched eagerly with a CUDA-event pair around every stage ----
     hp.profile(True)
+    hp.overlap = False            # one stream: a stage's events then bracket only its own kernels
     barrier()
     for i in range(a.steps):
         flush.zero_()
@@ -254,6 +255,7 @@ def run_b200(a):
     barrier()
     stage_ms = hp.stage_ms()
     hp.profile(False)
+    hp.overlap = True
 
     # ---- device-resident throughput: two steps in flight (HostPipeline slots fed from HBM-resident inputs) ----
     # No L2 flush is possible between overlapping steps; instead the rotating input sets together exceed the L2
@@ -341,7 +343,7 @@ def run_b200(a):
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
                          "flops_per_launch": alg[top] * B, "ms_per_launch": known[top]},
             "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
-            "launch_mode": "eager" if a.no_graph else "CUDA graph replay (stage_ms / roofline from an eager pass of the same steps)",
+            "launch_mode": "eager" if a.no_graph else "CUDA graph replay (stage_ms / roofline from an eager single-stream pass of the same steps)",
             "wall_ms_per_step_incl_flush": wall_ms / a.steps,
         }
         if not a.no_cpu_baseline and world == 1:

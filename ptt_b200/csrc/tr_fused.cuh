@@ -4,7 +4,8 @@
 #include "common.cuh"
 
 enum TrProducer { TR_PROD_PLAIN = 0, TR_PROD_DELTA0 = 1, TR_PROD_QKPOS = 2 };
-enum TrEpilogue { TR_EPI_STORE = 0, TR_EPI_SOFTMAX = 1 };
+// STORE_QK: out = relu(acc + bias + QG[token] - KG[neighbour])  (the q/k part of fc_gamma.0, pre-multiplied per token)
+enum TrEpilogue { TR_EPI_STORE = 0, TR_EPI_SOFTMAX = 1, TR_EPI_STORE_QK = 2 };
 
 struct TrPassArgs {
   int n = 0, k = 0, dm = 0;      // tokens per cloud, neighbours per token, d_model

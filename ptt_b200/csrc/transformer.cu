@@ -18,7 +18,12 @@ namespace {
 struct TrLayout {
   int dp, dm;
   // linear images (wt rows + bias row), in floats from the start of the params block
-  size_t fc1, qkv, delta0, delta2, gamma0, gamma2, fc2, total;
+  size_t fc1, qkv, delta0, delta2, gamma0, gamma2, fc2;
+  // fused path (tr_fused.cu): fc_gamma.0 is linear, so its q / k / pos parts are pre-multiplied at pack time:
+  //   qkg   : x -> [Wg0.Wq x | Wg0.Wk x | Wv x]      (replaces the q, k, v projection)
+  //   wprime: (Wg0.Wd2) as tcgen05 image, cprime = Wg0.bd2 + bg0
+  //   scratch: the three d x d products in fp32 (row-major), kept for inspection
+  size_t qkg, wprime, cprime, scratch, total;
 };
 
 bool tr_layout(int dp, int dm, TrLayout* L) {
@@ -38,8 +43,23 @@ bool tr_layout(int dp, int dm, TrLayout* L) {
   L->gamma0 = take(dm, dm);
   L->gamma2 = take(dm, dm);
   L->fc2 = take(dm, dp);
+  L->qkg = take(dm, 3 * round_up(dm, 4));
+  L->wprime = off; off += ptt_tc_weight_floats(dm, dm);
+  L->cprime = off; off += round_up(dm, 4);
+  L->scratch = off; off += (size_t)3 * dm * dm;
   L->total = off;
   return true;
+}
+
+// cprime[c] = sum_m Wg0[c, m] * bd2[m] + bg0[c]
+__global__ void tr_cprime_kernel(const float* __restrict__ wg0, const float* __restrict__ bd2, const float* __restrict__ bg0, int dm,
+                                 float* __restrict__ cprime) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= dm) return;
+  float acc = bg0 ? bg0[c] : 0.f;
+  if (bd2)
+    for (int m = 0; m < dm; ++m) acc = fmaf(wg0[(size_t)c * dm + m], bd2[m], acc);
+  cprime[c] = acc;
 }
 
 // h[(b,i,j), c] = relu(Wd0[c,:] . (xyz_i - xyz_knn(i,j)) + bd0[c])      delta0 image: 3 rows wt + bias row
@@ -176,7 +196,28 @@ extern "C" int ptt_transformer_pack_params(int d_points, int d_model, const floa
   if ((rc = tc_pack(L.gamma0, dm, dm))) return rc;
   if ((rc = tc_pack(L.gamma2, dm, dm))) return rc;
   if ((rc = tc_pack(L.fc2, dm, dp))) return rc;
-  return PTT_OK;
+  if (tr_fused_supported(1, 1, dm)) {
+    // products P[c, k] = sum_m Wg0[c, m] * W[m, k]: a row-block contraction with x = Wg0 (rows c) and the (m, k) matrix
+    // W used directly as the "transposed weight" image
+    float* sc = params + L.scratch;
+    auto product = [&](const float* w, float* dst) {
+      PttGemmArgs g;
+      g.x = gamma0_w; g.ldx = dm; g.R = dm; g.K = dm;
+      g.wt = w; g.ldw = dm; g.N = dm;
+      g.y = dst; g.ldy = dm;
+      return ptt_gemm_launch_ffma(g, st);
+    };
+    if ((rc = product(delta2_w, sc))) return rc;
+    if ((rc = product(wq, sc + (size_t)dm * dm))) return rc;
+    if ((rc = product(wk, sc + (size_t)2 * dm * dm))) return rc;
+    if ((rc = ptt_tc_pack_weight(sc, dm, 1, dm, dm, params + L.wprime, st))) return rc;
+    tr_cprime_kernel<<<ceil_div(dm, 128), 128, 0, st>>>(gamma0_w, delta2_b, gamma0_b, dm, params + L.cprime); PTT_LAUNCHED();
+    if ((rc = ptt_linear_pack_cols(sc + (size_t)dm * dm, nullptr, dm, dm, 3 * ld, 0, params + L.qkg, st))) return rc;
+    if ((rc = ptt_linear_pack_cols(sc + (size_t)2 * dm * dm, nullptr, dm, dm, 3 * ld, ld, params + L.qkg, st))) return rc;
+    if ((rc = ptt_linear_pack_cols(wv, nullptr, dm, dm, 3 * ld, 2 * ld, params + L.qkg, st))) return rc;
+    if ((rc = tc_pack(L.qkg, dm, 3 * ld))) return rc;
+  }
+  return ptt_launch_status();
 }
 
 extern "C" size_t ptt_transformer_block_workspace_bytes(int B, int n, int k, int d_points, int d_model) {
@@ -232,10 +273,12 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
     return ptt_gemm_launch(g, st);
   };
 
+  const bool fused = tr_fused_supported(n, k, dm);
   if ((rc = linear(features, dp, tokens, dp, L.fc1, dm, ld, true, 0, nullptr, 0, x, ld))) return rc;
-  if ((rc = linear(x, ld, tokens, dm, L.qkv, 3 * ld, 3 * ld, false, 0, nullptr, 0, qkv, ldq))) return rc;
+  // fused path: [Wg0.Wq x | Wg0.Wk x | Wv x]; generic path: [q | k | v]
+  if ((rc = linear(x, ld, tokens, dm, fused ? L.qkg : L.qkv, 3 * ld, 3 * ld, false, 0, nullptr, 0, qkv, ldq))) return rc;
 
-  if (tr_fused_supported(n, k, dm)) {
+  if (fused) {
     // ---- pair-row passes on the tensor cores with generated A operands and fused reductions (tr_fused.cu)
     auto img_w = [&](size_t img) { return params + img + (size_t)(dm + 1) * ld; };   // tcgen05 image behind the fp32 one
     auto img_b = [&](size_t img) { return params + img + (size_t)dm * ld; };         // bias row
@@ -247,10 +290,12 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
     p1.wd0 = params + L.delta0; p1.ldw0 = ld;
     p1.wimg = img_w(L.delta2); p1.bias = img_b(L.delta2); p1.relu = 0; p1.out = pos; p1.ldo = ld;
     if ((rc = tr_fused_launch(p1, TR_PROD_DELTA0, TR_EPI_STORE, st))) return rc;
-    // pass 2: g = relu(fc_gamma.0(q_i - k_j + pos))
+    // pass 2: g = relu(fc_gamma.0(q_i - k_j + pos)) = relu((Wg0.Wd2) h_ij + (Wg0 q)_i - (Wg0 k)_j + (Wg0 bd2 + bg0)):
+    // the A operand is the same generated h as in pass 1 (no loads); the per-token q / k parts are added in the epilogue
     TrPassArgs p2 = t;
-    p2.pos = pos; p2.wimg = img_w(L.gamma0); p2.bias = img_b(L.gamma0); p2.relu = 1; p2.out = h; p2.ldo = ld;
-    if ((rc = tr_fused_launch(p2, TR_PROD_QKPOS, TR_EPI_STORE, st))) return rc;
+    p2.wd0 = params + L.delta0; p2.ldw0 = ld;
+    p2.wimg = params + L.wprime; p2.bias = params + L.cprime; p2.relu = 1; p2.out = h; p2.ldo = ld;
+    if ((rc = tr_fused_launch(p2, TR_PROD_DELTA0, TR_EPI_STORE_QK, st))) return rc;
     // pass 3: logits = fc_gamma.2(g); softmax over the k neighbours; res = sum p * (v + pos)
     TrPassArgs p3 = t;
     p3.a_src = h; p3.lda = ld; p3.pos = pos; p3.wimg = img_w(L.gamma2); p3.bias = img_b(L.gamma2);

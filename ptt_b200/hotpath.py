@@ -65,6 +65,7 @@ class HotPath:
         self.box_tr = ops.PackedTransformer(_sub(sd, "box_voting_head.transformer_block."), self.cfg["knn"])
         self.streams = None
         self.use_graph = True         # forward_host replays a captured CUDA graph
+        self.overlap = True           # template branch on a second stream (False: one stream, for per-stage timing)
         self._ws = {}                 # persistent per-stage workspaces (no allocator traffic in steady state)
         self.stage_events = None      # set to {} to record (start, end) CUDA events per stage on its stream
 
@@ -149,7 +150,7 @@ class HotPath:
         if self.streams is None:
             self.streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         cur = torch.cuda.current_stream()
-        s1, s2 = self.streams
+        s1, s2 = self.streams if self.overlap else (self.streams[0], self.streams[0])
         s1.wait_stream(cur)
         s2.wait_stream(cur)
         with torch.cuda.stream(s2):      # template branch overlaps the search branch (independent clouds)
