@@ -10,10 +10,10 @@
 // activations are split on the fly by the producer warps while they stage the A tile in shared memory.
 //
 // CTA = 128 output rows x BN output columns; warp roles:
-//   warps 0-3  A producers (global fp32 rows, optional row gather -> fp16 hi/lo -> swizzled smem), then
-//              epilogue (TMEM -> registers -> scale/shift/ReLU/residual -> global)
-//   warp  4    weight loader: cp.async.bulk (TMA engine) of pre-swizzled 8 KB blocks, mbarrier complete_tx
-//   warp  5    TMEM allocation + the single thread that issues tcgen05.mma / tcgen05.commit
+//   warps 0-7  A producers (global fp32 rows, optional row gather -> fp16 hi/lo -> swizzled smem); warps 0-3 then run
+//              the epilogue (TMEM -> registers -> scale/shift/ReLU/residual -> global)
+//   warp  8    weight loader: cp.async.bulk (TMA engine) of pre-swizzled 8 KB blocks, mbarrier complete_tx
+//   warp  9    TMEM allocation + tcgen05.mma / tcgen05.commit issue (convergent warp, one elected lane)
 // K is consumed in 64-wide blocks through a 2-4 stage ring of (A hi, A lo, B hi, B lo) tiles.
 #include "gemm.cuh"
 #include "tc_common.cuh"
@@ -22,7 +22,7 @@ namespace {
 
 constexpr int TBM = 128;       // rows per CTA
 constexpr int TBK = 64;        // K per stage = one 128-byte swizzle row of fp16
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;       // 8 producer warps (the first 4 also run the epilogue) + loader + MMA
 constexpr uint32_t A_HALF_BYTES = TBM * TBK * 2;      // 16 KB
 constexpr uint32_t W_BLOCK_BYTES = 64 * TBK * 2;      // 8 KB: 64 weight rows x 64 k
 
@@ -74,23 +74,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(&full_a[s], TBM);
+      tc::mbar_init(&full_a[s], 256);
       tc::mbar_init(&full_b[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
     tc::mbar_init(accum_full, 1);
     tc::mbar_init_fence();
   }
-  if (warp == 5) tc::tmem_alloc(tmem_slot, BN);
+  if (warp == 9) tc::tmem_alloc(tmem_slot, BN);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ------------------------------------------------------------ A producers
     const int c4 = tid & 15;          // float4 column within the 64-wide k block
-    const int rsub = tid >> 4;        // 0..7
+    const int rsub = tid >> 4;        // 0..15
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < KB; ++kb) {
@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       uint8_t* a_hi = smem + stage * Cfg::STAGE_BYTES;
       uint8_t* a_lo = a_hi + A_HALF_BYTES;
       const int k = kb * TBK + c4 * 4;
-      float4 v[16];
+      float4 v[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int src = s_row[i * 8 + rsub];
+      for (int i = 0; i < 8; ++i) {
+        const int src = s_row[i * 16 + rsub];
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (src >= 0 && k < g.K) {
           const float* ptr = g.x + (size_t)src * g.ldx + k;
@@ -115,19 +115,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         }
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int r = i * 8 + rsub;
-        __half h[4], l[4];
-        tc::split_f16(v[i].x, h[0], l[0]);
-        tc::split_f16(v[i].y, h[1], l[1]);
-        tc::split_f16(v[i].z, h[2], l[2]);
-        tc::split_f16(v[i].w, h[3], l[3]);
-        const uint32_t off = tc::sw128_offset(r, c4 >> 1) + ((c4 & 1) << 3);
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 16 + rsub;
         uint2 ph, pl;
-        ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
-        ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
-        pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
-        pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+        tc::split_f16x2(v[i].x, v[i].y, ph.x, pl.x);
+        tc::split_f16x2(v[i].z, v[i].w, ph.y, pl.y);
+        const uint32_t off = tc::sw128_offset(r, c4 >> 1) + ((c4 & 1) << 3);
         *reinterpret_cast<uint2*>(a_hi + off) = ph;
         *reinterpret_cast<uint2*>(a_lo + off) = pl;
       }
@@ -135,7 +128,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       tc::mbar_arrive(&full_a[stage]);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
-
+  }
+  if (warp < 4) {
     // ------------------------------------------------------------ epilogue
     tc::mbar_wait(accum_full, 0);
     tc::tc_fence_after();
@@ -189,7 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ------------------------------------------------------------ weight loader (TMA engine)
     if (lane == 0) {
       int stage = 0;
@@ -211,7 +205,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
     {
       constexpr uint32_t IDESC = tc::idesc_f16<false>(TBM, BN);
@@ -242,7 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, BN);
   }
@@ -316,7 +310,11 @@ int ptt_tc_gemm_launch(const PttGemmArgs& a, const void* wimg, cudaStream_t st) 
   p.wimg = static_cast<const __half*>(wimg);
   p.n_wblocks = ceil_div(a.N, 64);
   p.k_blocks = ceil_div(a.K, 64);
-  if (a.N <= 64) return tc_launch<64>(p, st);
-  if (a.N <= 128) return tc_launch<128>(p, st);
+  // widest tile that still gives the grid at least one CTA per SM (small problems are latency-, not throughput-bound)
+  const long long row_tiles = ceil_div(a.R, TBM);
+  int bn = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
+  while (bn > 64 && row_tiles * ceil_div(a.N, bn) < 148) bn >>= 1;
+  if (bn == 64) return tc_launch<64>(p, st);
+  if (bn == 128) return tc_launch<128>(p, st);
   return tc_launch<256>(p, st);
 }
