@@ -253,7 +253,7 @@ def run_b200(a):
         flush.zero_()
         hp(search_d[i % n_sets], templ_d[i % n_sets])
     barrier()
-    stage_ms = hp.stage_ms()
+    stage_ms = hp.stage_ms(median=True)
     hp.profile(False)
     hp.overlap = True
 

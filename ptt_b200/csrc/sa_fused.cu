@@ -15,7 +15,7 @@
 //                 D2 (TMEM) -> +shift, ReLU -> fp16 hi/lo -> HB (smem, UMMA K-major SW128);
 //                 D3 (TMEM) -> +shift, ReLU -> max over each centre's ns rows (redux.sync) -> out (B, M, D3)
 //   warps 8-15  producers: per-row (point index, rel xyz) -> gather G' -> layer 1 -> fp16 hi/lo -> HA (smem)
-//   warp  16    weight loader: W2 / W3 as 16 KB (64 out-channels x 64 k, hi+lo) blocks through a 5-stage ring (TMA engine)
+//   warp  16    weight loader: W2 / W3 as (k-block, <=128 out-channels) items through a 3-stage ring (TMA engine)
 //   warp  17    TMEM allocation + the single thread issuing tcgen05.mma / tcgen05.commit
 // BatchNorm scales of layers 2 and 3 are folded into the packed weights, so both epilogues are acc + shift.
 #include "sa_fused.cuh"
@@ -25,32 +25,46 @@ namespace {
 
 constexpr int SF_THREADS = 576;            // 8 epilogue + 8 producer warps + loader + MMA
 constexpr int SF_TM = 128;
-constexpr int SF_NS = 5;                       // ring stages
-constexpr uint32_t SF_ITEM_BYTES = 16384;      // one weight block: 64 rows x 64 k, hi (8 KB) + lo (8 KB)
+constexpr int SF_NS = 3;                       // ring stages
+constexpr uint32_t SF_STAGE_BYTES = 32768;     // one weight item: <=128 rows x 64 k, hi + lo
 constexpr uint32_t SF_KBLOCK_BYTES = 32768;    // one activation k-block: 128 rows x 64 k, hi (16 KB) + lo (16 KB)
 
 template <int D1, int D2, int D3>
 struct SfCfg {
-  static constexpr int KB1 = D1 / 64, KB2 = D2 / 64, NB2 = D2 / 64, NB3 = D3 / 64;
+  static constexpr int KB1 = D1 / 64, KB2 = D2 / 64;
+  static constexpr int NI2 = D2 < 128 ? D2 : 128, NI3 = D3 < 128 ? D3 : 128;   // MMA N / rows per weight item
+  static constexpr int ITEMS2 = D2 / NI2, ITEMS3 = D3 / NI3;                   // items per k-block
   static constexpr uint32_t HA_BYTES = KB1 * SF_KBLOCK_BYTES;
   static constexpr uint32_t HB_BYTES = KB2 * SF_KBLOCK_BYTES;
-  static constexpr uint32_t RING_BYTES = SF_NS * SF_ITEM_BYTES;
-  static constexpr uint32_t CTRL_BYTES = 256 + 128 * 16 + (D2 + D3) * 4;
-  static constexpr uint32_t SMEM_BYTES = HA_BYTES + HB_BYTES + RING_BYTES + CTRL_BYTES + 1024;
+  static constexpr uint32_t RING_BYTES = SF_NS * SF_STAGE_BYTES;
+  static constexpr uint32_t CTRL_BYTES = 256 + 128 * 16;
+  static constexpr uint32_t SMEM_BYTES = HA_BYTES + HB_BYTES + RING_BYTES + CTRL_BYTES;   // 231,680 B at (128,128,256)
   static constexpr uint32_t D2_COL = 0, D3_COL = 128, TMEM_COLS = 512;
 };
 
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack2(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+// weight item (kb, ni) of a (Dout, K) image made of 8 KB (64 rows x 64 k) hi / lo blocks -> one ring stage laid out
+// [hi rows 0..NI) | lo rows 0..NI)]
+template <int NI>
+__device__ __forceinline__ void sf_load_item(uint8_t* dst, const uint8_t* img, int KB, int kb, int ni, uint64_t* bar) {
+  tc::mbar_arrive_expect_tx(bar, NI * 256);
+  if (NI == 128) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint8_t* src = img + (size_t)((ni * 2 + j) * KB + kb) * 16384;
+      tc::bulk_g2s(dst + j * 8192, src, 8192, bar);
+      tc::bulk_g2s(dst + 16384 + j * 8192, src + 8192, 8192, bar);
+    }
+  } else {
+    tc::bulk_g2s(dst, img + (size_t)(ni * KB + kb) * 16384, 16384, bar);
+  }
 }
 
 template <int D1, int D2, int D3>
 __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_constant__ SaFusedArgs a, const int num_tiles) {
   using Cfg = SfCfg<D1, D2, D3>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* HA = smem;
   uint8_t* HB = HA + Cfg::HA_BYTES;
   uint8_t* ring = HB + Cfg::HB_BYTES;
@@ -60,17 +74,14 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
   uint64_t* ha_full = empty + SF_NS;
   uint64_t* ha_free = ha_full + 1;
   uint64_t* d2_full = ha_free + 1;
-  uint64_t* hb_full = d2_full + 1;
-  uint64_t* d3_full = hb_full + 1;
+  uint64_t* hb_full = d2_full + 1;                         // [KB2]: H2 is handed over k-block by k-block
+  uint64_t* d3_full = hb_full + Cfg::KB2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d3_full + 1);
   float4* s_info = reinterpret_cast<float4*>(ctrl + 256);                 // [128] {rel.xyz, point row as int bits}
-  float* s_sh2 = reinterpret_cast<float*>(ctrl + 256 + 128 * 16);         // [D2]
-  float* s_sh3 = s_sh2 + D2;                                              // [D3]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();          // the UMMA tiles need 1024-byte alignment
 
-  for (int c = tid; c < D2; c += SF_THREADS) s_sh2[c] = __ldg(a.shift2 + c);
-  for (int c = tid; c < D3; c += SF_THREADS) s_sh3[c] = __ldg(a.shift3 + c);
   if (tid == 0) {
     for (int s = 0; s < SF_NS; ++s) {
       tc::mbar_init(&full_b[s], 1);
@@ -79,7 +90,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     tc::mbar_init(ha_full, 256);
     tc::mbar_init(ha_free, 1);
     tc::mbar_init(d2_full, 1);
-    tc::mbar_init(hb_full, 256);
+    for (int s = 0; s < Cfg::KB2; ++s) tc::mbar_init(&hb_full[s], 256);
     tc::mbar_init(d3_full, 1);
     tc::mbar_init_fence();
   }
@@ -99,36 +110,44 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t par = it & 1;
-      // ---- E2: D2 -> H2 (HB)
+      const bool erec = a.dbg != nullptr && blockIdx.x == 0 && tid == 0 && it < 30;
+      // ---- E2: D2 -> H2 (HB), one 64-column k-block at a time so that layer 3 can start on the first one
       tc::mbar_wait(d2_full, par);
       tc::tc_fence_after();
+      if (erec) a.dbg[1000 + it * 4 + 0] = clock64();
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < D2; c0 += 64) {
+      for (int kb = 0; kb < Cfg::KB2; ++kb) {
+        const int c0 = kb * 64 + half * 32;
         float v[32];
         tc::tmem_ld32(lane_addr + Cfg::D2_COL + (uint32_t)c0, v);
-        uint8_t* blk = HB + (c0 >> 6) * SF_KBLOCK_BYTES;
-        const int chunk0 = (c0 & 63) >> 3;
+        uint8_t* blk = HB + kb * SF_KBLOCK_BYTES;
+        const int chunk0 = half * 4;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          __half hi[8], lo[8];
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.shift2 + c0 + ch * 8));
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.shift2 + c0 + ch * 8 + 4));
+          const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          float h[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float h = fmaxf(v[ch * 8 + u] + s_sh2[c0 + ch * 8 + u], 0.f);
-            tc::split_f16(h, hi[u], lo[u]);
-          }
+          for (int u = 0; u < 8; ++u) h[u] = fmaxf(v[ch * 8 + u] + sh[u], 0.f);
+          uint4 hi, lo;
+          tc::split_f16x2(h[0], h[1], hi.x, lo.x);
+          tc::split_f16x2(h[2], h[3], hi.y, lo.y);
+          tc::split_f16x2(h[4], h[5], hi.z, lo.z);
+          tc::split_f16x2(h[6], h[7], hi.w, lo.w);
           const uint32_t off = tc::sw128_offset(r, chunk0 + ch);
-          *reinterpret_cast<uint4*>(blk + off) =
-              make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
-          *reinterpret_cast<uint4*>(blk + 16384 + off) =
-              make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+          *reinterpret_cast<uint4*>(blk + off) = hi;
+          *reinterpret_cast<uint4*>(blk + 16384 + off) = lo;
         }
+        tc::tc_fence_before();
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&hb_full[kb]);
       }
-      tc::tc_fence_before();
-      tc::fence_proxy_async_smem();
-      tc::mbar_arrive(hb_full);
+      if (erec) a.dbg[1000 + it * 4 + 1] = clock64();
       // ---- E3: D3 -> max over each centre's rows -> out
       tc::mbar_wait(d3_full, par);
       tc::tc_fence_after();
+      if (erec) a.dbg[1000 + it * 4 + 2] = clock64();
       const long long R = (long long)tile * SF_TM + r;
       const bool writer = (lane & (ns - 1)) == 0 && R < a.rows;
       float* orow = a.out_pm + (R / ns) * (long long)a.ld_out;
@@ -137,10 +156,15 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         float v[32];
         tc::tmem_ld32(lane_addr + Cfg::D3_COL + (uint32_t)c0, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float y = v[j] + s_sh3[c0 + j];
-          y = y > 0.f ? y : 0.f;                               // ReLU; exactly +0 so that uint order == float order
-          v[j] = __uint_as_float(__reduce_max_sync(gmask, __float_as_uint(y)));
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift3 + c0 + j));
+          const float s4[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float y = v[j + u] + s4[u];
+            y = y > 0.f ? y : 0.f;                             // ReLU; exactly +0 so that uint order == float order
+            v[j + u] = __uint_as_float(__reduce_max_sync(gmask, __float_as_uint(y)));
+          }
         }
         if (writer) {
 #pragma unroll
@@ -148,6 +172,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         }
       }
       tc::tc_fence_before();
+      if (erec) a.dbg[1000 + it * 4 + 3] = clock64();
     }
   } else if (warp < 16) {
     // =================================================================== producers: layer 1 on CUDA cores
@@ -165,27 +190,41 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         for (int d = 0; d < 3; ++d) wx[h][d][u] = __ldg(a.wx + d * D1 + c);
         g0[h][u] = a.gprime ? 0.f : __ldg(a.shift1 + c);
       }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      // per-row neighbour info
-      producer_bar();                                   // everyone is done reading s_info of the previous tile
-      if (pt < SF_TM) {
+    // Per-row neighbour info is software-pipelined: the dependent global loads (ball-query index -> point) of tile
+    // t+1 are issued before H1 of tile t is written, so their latency never sits on the producers' critical path.
+    auto row_index = [&](int tile) -> int {          // ball-query result of this thread's row, -1 beyond the end
+      const long long R = (long long)tile * SF_TM + pt;
+      return (pt < SF_TM && tile < num_tiles && R < a.rows) ? __ldg(a.idx + R) : -1;
+    };
+    auto row_info = [&](int tile, int i) -> float4 {
+      float4 info = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      if (i >= 0) {
         const long long R = (long long)tile * SF_TM + pt;
-        float4 info = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        if (R < a.rows) {
-          const long long cj = R / ns;
-          const long long b = cj / a.M;
-          const long long src = b * a.N + __ldg(a.idx + R);
-          const float* p = a.xyz + src * 3;
-          const float* c = a.new_xyz + cj * 3;
-          float dx = __fsub_rn(__ldg(p), __ldg(c)), dy = __fsub_rn(__ldg(p + 1), __ldg(c + 1)), dz = __fsub_rn(__ldg(p + 2), __ldg(c + 2));
-          if (a.normalize) { dx = __fdiv_rn(dx, a.radius); dy = __fdiv_rn(dy, a.radius); dz = __fdiv_rn(dz, a.radius); }
-          info = make_float4(dx, dy, dz, __int_as_float((int)src));
-        }
-        s_info[pt] = info;
+        const long long cj = R / ns;
+        const long long src = (cj / a.M) * a.N + i;
+        const float* p = a.xyz + src * 3;
+        const float* c = a.new_xyz + cj * 3;
+        float dx = __fsub_rn(__ldg(p), __ldg(c)), dy = __fsub_rn(__ldg(p + 1), __ldg(c + 1)), dz = __fsub_rn(__ldg(p + 2), __ldg(c + 2));
+        if (a.normalize) { dx = __fdiv_rn(dx, a.radius); dy = __fdiv_rn(dy, a.radius); dz = __fdiv_rn(dz, a.radius); }
+        info = make_float4(dx, dy, dz, __int_as_float((int)src));
       }
+      return info;
+    };
+    const int stride = gridDim.x;
+    int idx_next = row_index(blockIdx.x + stride);              // index for tile t+1
+    float4 info_cur = row_info(blockIdx.x, row_index(blockIdx.x));
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += stride, ++it) {
+      producer_bar();                                   // everyone is done reading s_info of the previous tile
+      if (pt < SF_TM) s_info[pt] = info_cur;
       producer_bar();
+      // issue the loads for the next two tiles now; they are consumed after this tile's H1 has been written
+      const float4 info_nxt = row_info(tile + stride, idx_next);
+      const int idx_nn = row_index(tile + 2 * stride);
+      const bool prec = a.dbg != nullptr && blockIdx.x == 0 && pt == 0 && it < 30;
+      if (prec) a.dbg[2000 + it * 3 + 0] = clock64();
       tc::mbar_wait(ha_free, (uint32_t)(it & 1) ^ 1u);  // GEMM2 of the previous tile has consumed HA
+      if (prec) a.dbg[2000 + it * 3 + 1] = clock64();
 #pragma unroll 4
       for (int i = 0; i < 8; ++i) {
         const int r = i * 16 + rsub;
@@ -196,23 +235,27 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
           float4 g = make_float4(g0[h][0], g0[h][1], g0[h][2], g0[h][3]);
           if (a.gprime != nullptr && src >= 0) g = __ldg(reinterpret_cast<const float4*>(a.gprime + (size_t)src * D1 + (q + 16 * h) * 4));
           float y[4] = {g.x, g.y, g.z, g.w};
-          __half hi[4], lo[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             float t = fmaf(wx[h][0][u], info.x, y[u]);
             t = fmaf(wx[h][1][u], info.y, t);
             t = fmaf(wx[h][2][u], info.z, t);
-            t = src >= 0 ? fmaxf(t, 0.f) : 0.f;
-            tc::split_f16(t, hi[u], lo[u]);
+            y[u] = src >= 0 ? fmaxf(t, 0.f) : 0.f;
           }
+          uint2 hi, lo;
+          tc::split_f16x2(y[0], y[1], hi.x, lo.x);
+          tc::split_f16x2(y[2], y[3], hi.y, lo.y);
           uint8_t* blk = HA + h * SF_KBLOCK_BYTES;
           const uint32_t off = tc::sw128_offset(r, q >> 1) + ((q & 1) << 3);
-          *reinterpret_cast<uint2*>(blk + off) = make_uint2(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]));
-          *reinterpret_cast<uint2*>(blk + 16384 + off) = make_uint2(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]));
+          *reinterpret_cast<uint2*>(blk + off) = hi;
+          *reinterpret_cast<uint2*>(blk + 16384 + off) = lo;
         }
       }
       tc::fence_proxy_async_smem();
+      if (prec) a.dbg[2000 + it * 3 + 2] = clock64();
       tc::mbar_arrive(ha_full);
+      info_cur = info_nxt;
+      idx_next = idx_nn;
     }
   } else if (warp == 16) {
     // =================================================================== weight loader
@@ -223,19 +266,15 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       const uint8_t* w3 = static_cast<const uint8_t*>(a.w3img);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 #pragma unroll 1
-        for (int item = 0; item < Cfg::KB1 * Cfg::NB2 + Cfg::KB2 * Cfg::NB3; ++item) {
-          const uint8_t* src;
-          if (item < Cfg::KB1 * Cfg::NB2) {
-            const int kb = item / Cfg::NB2, nb = item % Cfg::NB2;
-            src = w2 + (size_t)(nb * Cfg::KB1 + kb) * SF_ITEM_BYTES;
-          } else {
-            const int j = item - Cfg::KB1 * Cfg::NB2;
-            const int kb = j / Cfg::NB3, nb = j % Cfg::NB3;
-            src = w3 + (size_t)(nb * Cfg::KB2 + kb) * SF_ITEM_BYTES;
-          }
+        for (int item = 0; item < Cfg::KB1 * Cfg::ITEMS2 + Cfg::KB2 * Cfg::ITEMS3; ++item) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
-          tc::mbar_arrive_expect_tx(&full_b[stage], SF_ITEM_BYTES);
-          tc::bulk_g2s(ring + stage * SF_ITEM_BYTES, src, SF_ITEM_BYTES, &full_b[stage]);
+          uint8_t* dst = ring + stage * SF_STAGE_BYTES;
+          if (item < Cfg::KB1 * Cfg::ITEMS2) {
+            sf_load_item<Cfg::NI2>(dst, w2, Cfg::KB1, item / Cfg::ITEMS2, item % Cfg::ITEMS2, &full_b[stage]);
+          } else {
+            const int j = item - Cfg::KB1 * Cfg::ITEMS2;
+            sf_load_item<Cfg::NI3>(dst, w3, Cfg::KB2, j / Cfg::ITEMS3, j % Cfg::ITEMS3, &full_b[stage]);
+          }
           if (++stage == SF_NS) { stage = 0; phase ^= 1; }
         }
       }
@@ -243,33 +282,39 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
   } else {
     // =================================================================== MMA issuer (whole warp, one elected lane issues)
     {
-      constexpr uint32_t IDESC = tc::idesc_f16<false>(SF_TM, 64);
+      constexpr uint32_t IDESC2 = tc::idesc_f16<false>(SF_TM, Cfg::NI2);
+      constexpr uint32_t IDESC3 = tc::idesc_f16<false>(SF_TM, Cfg::NI3);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       const uint32_t ha_addr = tc::smem_u32(HA), hb_addr = tc::smem_u32(HB), ring_addr = tc::smem_u32(ring);
+      const bool rec = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+      int nrec = 0;
+      auto stamp = [&](int tag) { if (rec && nrec < 300) { a.dbg[2 * nrec] = tag; a.dbg[2 * nrec + 1] = clock64(); ++nrec; } };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t par = it & 1;
         // ---- layer 2: D2 = H1 . W2'^T
+        stamp(1);
         tc::mbar_wait(ha_full, par);
         tc::tc_fence_after();
+        stamp(2);
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB1; ++kb) {
 #pragma unroll 1
-          for (int nb = 0; nb < Cfg::NB2; ++nb) {
+          for (int ni = 0; ni < Cfg::ITEMS2; ++ni) {
             tc::mbar_wait(&full_b[stage], phase);
             tc::tc_fence_after();
             const uint64_t da_hi = tc::smem_desc_sw128(ha_addr + kb * SF_KBLOCK_BYTES);
             const uint64_t da_lo = tc::smem_desc_sw128(ha_addr + kb * SF_KBLOCK_BYTES + 16384);
-            const uint64_t db_hi = tc::smem_desc_sw128(ring_addr + stage * SF_ITEM_BYTES);
-            const uint64_t db_lo = tc::smem_desc_sw128(ring_addr + stage * SF_ITEM_BYTES + 8192);
-            const uint32_t d = tmem_base + Cfg::D2_COL + nb * 64;
+            const uint64_t db_hi = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES);
+            const uint64_t db_lo = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES + Cfg::NI2 * 128);
+            const uint32_t d = tmem_base + Cfg::D2_COL + ni * Cfg::NI2;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);
-              tc::mma_f16_w(d, da_hi + adv, db_hi + adv, IDESC, (kb | k) != 0);
-              tc::mma_f16_w(d, da_lo + adv, db_hi + adv, IDESC, 1);
-              tc::mma_f16_w(d, da_hi + adv, db_lo + adv, IDESC, 1);
+              tc::mma_f16_w(d, da_hi + adv, db_hi + adv, IDESC2, (kb | k) != 0);
+              tc::mma_f16_w(d, da_lo + adv, db_hi + adv, IDESC2, 1);
+              tc::mma_f16_w(d, da_hi + adv, db_lo + adv, IDESC2, 1);
             }
             tc::mma_commit_w(&empty[stage]);
             if (++stage == SF_NS) { stage = 0; phase ^= 1; }
@@ -277,33 +322,37 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         }
         tc::mma_commit_w(ha_free);
         tc::mma_commit_w(d2_full);
-        // ---- layer 3: D3 = H2 . W3'^T
-        tc::mbar_wait(hb_full, par);
-        tc::tc_fence_after();
+        stamp(3);
+        // ---- layer 3: D3 = H2 . W3'^T, k-block by k-block as the epilogue hands H2 over
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB2; ++kb) {
+          tc::mbar_wait(&hb_full[kb], par);
+          tc::tc_fence_after();
+          if (kb == 0) stamp(4);
 #pragma unroll 1
-          for (int nb = 0; nb < Cfg::NB3; ++nb) {
+          for (int ni = 0; ni < Cfg::ITEMS3; ++ni) {
             tc::mbar_wait(&full_b[stage], phase);
             tc::tc_fence_after();
             const uint64_t da_hi = tc::smem_desc_sw128(hb_addr + kb * SF_KBLOCK_BYTES);
             const uint64_t da_lo = tc::smem_desc_sw128(hb_addr + kb * SF_KBLOCK_BYTES + 16384);
-            const uint64_t db_hi = tc::smem_desc_sw128(ring_addr + stage * SF_ITEM_BYTES);
-            const uint64_t db_lo = tc::smem_desc_sw128(ring_addr + stage * SF_ITEM_BYTES + 8192);
-            const uint32_t d = tmem_base + Cfg::D3_COL + nb * 64;
+            const uint64_t db_hi = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES);
+            const uint64_t db_lo = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES + Cfg::NI3 * 128);
+            const uint32_t d = tmem_base + Cfg::D3_COL + ni * Cfg::NI3;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);
-              tc::mma_f16_w(d, da_hi + adv, db_hi + adv, IDESC, (kb | k) != 0);
-              tc::mma_f16_w(d, da_lo + adv, db_hi + adv, IDESC, 1);
-              tc::mma_f16_w(d, da_hi + adv, db_lo + adv, IDESC, 1);
+              tc::mma_f16_w(d, da_hi + adv, db_hi + adv, IDESC3, (kb | k) != 0);
+              tc::mma_f16_w(d, da_lo + adv, db_hi + adv, IDESC3, 1);
+              tc::mma_f16_w(d, da_hi + adv, db_lo + adv, IDESC3, 1);
             }
             tc::mma_commit_w(&empty[stage]);
             if (++stage == SF_NS) { stage = 0; phase ^= 1; }
           }
         }
         tc::mma_commit_w(d3_full);
+        stamp(5);
       }
+      if (rec) a.dbg[2 * nrec] = -1;
     }
   }
 
@@ -336,13 +385,18 @@ int sf_launch(const SaFusedArgs& a, cudaStream_t st) {
 
 }  // namespace
 
+long long* g_sa_dbg = nullptr;   // tuning hook: timeline buffer picked up by the next launches (ptt_debug_sa_timeline)
+extern "C" __attribute__((visibility("default"))) void ptt_debug_sa_timeline(long long* buf) { g_sa_dbg = buf; }
+
 bool sa_fused_supported(int d1, int d2, int d3, int ns) {
   const bool dims = (d1 == 64 && d2 == 64 && d3 == 128) || (d1 == 128 && d2 == 128 && d3 == 256);
   const bool group = ns >= 1 && ns <= 32 && (ns & (ns - 1)) == 0;
   return dims && group;
 }
 
-int sa_fused_launch(const SaFusedArgs& a, int d1, int d2, int d3, cudaStream_t st) {
+int sa_fused_launch(const SaFusedArgs& a_in, int d1, int d2, int d3, cudaStream_t st) {
+  SaFusedArgs a = a_in;
+  a.dbg = g_sa_dbg;
   if (a.rows <= 0) return PTT_OK;
   if (d1 == 64 && d2 == 64 && d3 == 128) return sf_launch<64, 64, 128>(a, st);
   if (d1 == 128 && d2 == 128 && d3 == 256) return sf_launch<128, 128, 256>(a, st);

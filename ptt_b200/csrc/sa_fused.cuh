@@ -20,6 +20,7 @@ struct SaFusedArgs {
   float* out_pm = nullptr;         // (B*M, ld_out), D3 valid columns
   int ld_out = 0;
   long long rows = 0;              // B * M * ns
+  long long* dbg = nullptr;        // optional clock64 timeline of CTA 0 (tuning only)
 };
 
 bool sa_fused_supported(int d1, int d2, int d3, int ns);

@@ -80,9 +80,13 @@ class HotPath:
     def profile(self, on=True):
         self.stage_events = {} if on else None
 
-    def stage_ms(self):
-        """Mean milliseconds per stage over the recorded steps (call after a synchronize)."""
-        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in (self.stage_events or {}).items()}
+    def stage_ms(self, median=False):
+        """Mean (or median) milliseconds per stage over the recorded steps (call after a synchronize)."""
+        out = {}
+        for k, v in (self.stage_events or {}).items():
+            ts = sorted(a.elapsed_time(b) for a, b in v)
+            out[k] = ts[len(ts) // 2] if median else sum(ts) / len(ts)
+        return out
 
     class _Stage:
         def __init__(self, hp, name):
