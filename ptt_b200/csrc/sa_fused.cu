@@ -37,8 +37,8 @@ struct SfCfg {
   static constexpr uint32_t HA_BYTES = KB1 * SF_KBLOCK_BYTES;
   static constexpr uint32_t HB_BYTES = KB2 * SF_KBLOCK_BYTES;
   static constexpr uint32_t RING_BYTES = SF_NS * SF_STAGE_BYTES;
-  static constexpr uint32_t CTRL_BYTES = 256 + 128 * 16;
-  static constexpr uint32_t SMEM_BYTES = HA_BYTES + HB_BYTES + RING_BYTES + CTRL_BYTES;   // 231,680 B at (128,128,256)
+  static constexpr uint32_t CTRL_BYTES = 256 + 128 * 16 + D2 * 4;
+  static constexpr uint32_t SMEM_BYTES = HA_BYTES + HB_BYTES + RING_BYTES + CTRL_BYTES;   // 232,192 B at (128,128,256): 256 B under the 227 KB limit
   static constexpr uint32_t D2_COL = 0, D3_COL = 128, TMEM_COLS = 512;
 };
 
@@ -78,9 +78,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
   uint64_t* d3_full = hb_full + Cfg::KB2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d3_full + 1);
   float4* s_info = reinterpret_cast<float4*>(ctrl + 256);                 // [128] {rel.xyz, point row as int bits}
+  float* s_sh2 = reinterpret_cast<float*>(ctrl + 256 + 128 * 16);         // [D2] (shift3 stays in global: E3 is off the critical path)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((tc::smem_u32(smem) & 1023u) != 0) __trap();          // the UMMA tiles need 1024-byte alignment
+  for (int c = tid; c < D2; c += SF_THREADS) s_sh2[c] = __ldg(a.shift2 + c);
 
   if (tid == 0) {
     for (int s = 0; s < SF_NS; ++s) {
@@ -124,8 +126,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         const int chunk0 = half * 4;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.shift2 + c0 + ch * 8));
-          const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.shift2 + c0 + ch * 8 + 4));
+          const float4 s0 = *reinterpret_cast<const float4*>(s_sh2 + c0 + ch * 8);
+          const float4 s1 = *reinterpret_cast<const float4*>(s_sh2 + c0 + ch * 8 + 4);
           const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
           float h[8];
 #pragma unroll
