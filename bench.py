@@ -88,7 +88,7 @@ def algorithmic(a):
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -237,7 +237,6 @@ def run_b200(a):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop()
     dev_ms = sum(x.elapsed_time(y) for x, y in ev)
     if not a.no_graph:
         # graph replays do not pass through the library's host entry points: count what one replay launches
@@ -279,6 +278,7 @@ def run_b200(a):
     p1.record()
     barrier()
     pipe_ms = p0.elapsed_time(p1)
+    clocks = sampler.stop()        # sampled over both device-timed regions (sequential + pipelined)
 
     # ---- end-to-end through the host API: pinned host in, pinned host out, copies inside the timed region ----
     # HostPipeline = the throughput form of HotPath.forward_host: two instances alternate, so the H2D copy and compute
@@ -324,6 +324,10 @@ def run_b200(a):
             peaks = json.load(open(pk))
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         achieved_tf = alg[top] * B / (known[top] * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(REPO, "profiles", "r1_traffic.json")     # dram__bytes_read+write per launch from the ncu --set full capture
+        if os.path.exists(tp) and B == 48 and a.nsearch == 1024:
+            traffic = json.load(open(tp)).get(top)
         line = {
             "metric": METRIC, "value": shard.whole_job_throughput(B * a.steps, n_gpus, pipe_ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": pipe_ms / a.steps,
@@ -339,7 +343,8 @@ def run_b200(a):
                                                 "ms_per_step": e2e_sync_s * 1e3 / a.steps, "api": "HotPath.forward_host"}},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": top, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "frac": achieved_tf / peak_tf, "traffic": traffic,
+                         "frac_ceiling": "1/3: fp32-class accuracy costs 3 fp16 MMAs per algorithmic MAC (DESIGN.md 4)",
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
                          "flops_per_launch": alg[top] * B, "ms_per_launch": known[top]},
             "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
