@@ -24,6 +24,8 @@ struct TrPassArgs {
   const void* wimg = nullptr;    // tcgen05 image of the (dm, dm) weight
   const float* bias = nullptr;   // (dm)
   int relu = 0;
+  int qk_mode = 0;               // STORE_QK epilogue: 0 = + qkv[token, 0:] - qkv[nbr, koff:] ; 1 = + qkv[nbr, koff:] only
+  int pos_has_v = 0;             // SOFTMAX epilogue: `pos` already holds pos + v[nbr] (pass 1 ran with qk_mode 1)
   // outputs
   float* out = nullptr;          // STORE: (pairs, ldo);  SOFTMAX: res (B*n, ldo)
   int ldo = 0;

@@ -285,11 +285,13 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
     TrPassArgs t;
     t.n = n; t.k = k; t.dm = dm; t.pairs = pairs; t.xyz = xyz; t.knn = knn;
     t.qkv = qkv; t.ldq = ldq; t.koff = ld; t.voff = 2 * ld; t.divisor = sqrtf((float)dm);
-    // pass 1: pos = fc_delta.2(relu(fc_delta.0(xyz_i - xyz_j)))
+    // pass 1: pos = fc_delta.2(relu(fc_delta.0(xyz_i - xyz_j))); what is stored is pos_ij + v_j, the only form in which
+    // pos is used again (by the aggregation of pass 3)
     TrPassArgs p1 = t;
     p1.wd0 = params + L.delta0; p1.ldw0 = ld;
     p1.wimg = img_w(L.delta2); p1.bias = img_b(L.delta2); p1.relu = 0; p1.out = pos; p1.ldo = ld;
-    if ((rc = tr_fused_launch(p1, TR_PROD_DELTA0, TR_EPI_STORE, st))) return rc;
+    p1.koff = 2 * ld; p1.qk_mode = 1;
+    if ((rc = tr_fused_launch(p1, TR_PROD_DELTA0, TR_EPI_STORE_QK, st))) return rc;
     // pass 2: g = relu(fc_gamma.0(q_i - k_j + pos)) = relu((Wg0.Wd2) h_ij + (Wg0 q)_i - (Wg0 k)_j + (Wg0 bd2 + bg0)):
     // the A operand is the same generated h as in pass 1 (no loads); the per-token q / k parts are added in the epilogue
     TrPassArgs p2 = t;
@@ -299,7 +301,7 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
     // pass 3: logits = fc_gamma.2(g); softmax over the k neighbours; res = sum p * (v + pos)
     TrPassArgs p3 = t;
     p3.a_src = h; p3.lda = ld; p3.pos = pos; p3.wimg = img_w(L.gamma2); p3.bias = img_b(L.gamma2);
-    p3.out = res; p3.ldo = ld; p3.attn = attn_or_null;
+    p3.out = res; p3.ldo = ld; p3.attn = attn_or_null; p3.pos_has_v = 1;
     if (variant == 1) { p3.x_sub = x; p3.ldx = ld; }
     if ((rc = tr_fused_launch(p3, TR_PROD_PLAIN, TR_EPI_SOFTMAX, st))) return rc;
     return linear(res, ld, tokens, dm, L.fc2, dp, round_up(dp, 4), true, 0, features, dp, out, dp);

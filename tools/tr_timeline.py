@@ -6,6 +6,7 @@ from ptt_b200 import _lib, ops, synth
 
 cs = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 B, n, k, dm = 48, 128, 16, 512
 L = _lib.lib()
 L.ptt_debug_set_cluster.argtypes = [ctypes.c_int]
@@ -13,7 +14,7 @@ L.ptt_debug_set_cluster(cs)
 fn = L.ptt_debug_tr_pass_timeline
 fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
-                                                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+                                                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
 xyz = torch.from_numpy(synth.make_clouds(B, n, 1, "dense", role="template")).cuda()
 knn = ops.knn(xyz, k)
 w = torch.randn(dm, dm, device="cuda") / dm ** 0.5
@@ -21,6 +22,8 @@ b = torch.randn(dm, device="cuda")
 lin = ops.PackedLinear(w, b)
 wd0 = torch.randn(4, dm, device="cuda")
 out = torch.empty(B * n * k, dm, device="cuda")
+aux = torch.randn(B * n, 3 * dm, device="cuda")
+big = torch.randn(B * n * k, dm, device="cuda")
 dbg = torch.zeros(6000, dtype=torch.int64, device="cuda")
 ldw = dm
 wimg_ptr = lin.params.data_ptr() + (dm + 1) * ldw * 4
@@ -29,11 +32,11 @@ for rep in range(3):
     dbg.zero_()
     e0.record()
     rc = fn(xyz.data_ptr(), knn.data_ptr(), B, n, k, dm, wd0.data_ptr(), dm, wimg_ptr, b.data_ptr(), out.data_ptr(), dbg.data_ptr(), flags,
-            torch.cuda.current_stream().cuda_stream)
+            torch.cuda.current_stream().cuda_stream, mode, aux.data_ptr(), big.data_ptr())
     e1.record()
     torch.cuda.synchronize()
     assert rc == 0, rc
-print("kernel ms:", e0.elapsed_time(e1), "flags", flags)
+print("kernel ms:", e0.elapsed_time(e1), "flags", flags, "mode", mode)
 d = dbg.cpu().numpy()
 t0 = None
 ev = []
