@@ -170,6 +170,22 @@ PTT_API int ptt_transformer_block_fwd(const float* xyz, const float* features, i
                               float* out, float* attn_or_null, void* workspace, size_t workspace_bytes,
                               ptt_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * a10 TransformerBlockSTD.forward (dense n x n dot-product attention)   transformer_block/variants.py:12-40
+ *   features (B,n,d_points) -> out (B,n,d_points); attn (B,n,n) or NULL.  Parameter tensors are the reference
+ *   state_dict entries fc1, fc2, fc_delta.{0,2} (weight + bias) and w_qs, w_ks, w_vs (weight).
+ * ------------------------------------------------------------------------------------------- */
+PTT_API size_t ptt_transformer_std_params_floats(int d_points, int d_model);
+PTT_API int ptt_transformer_std_pack_params(int d_points, int d_model, const float* fc1_w, const float* fc1_b,
+                                    const float* fc2_w, const float* fc2_b, const float* delta0_w,
+                                    const float* delta0_b, const float* delta2_w, const float* delta2_b,
+                                    const float* wq, const float* wk, const float* wv, float* params,
+                                    ptt_stream_t stream);
+PTT_API size_t ptt_transformer_std_workspace_bytes(int B, int n, int d_points, int d_model);
+PTT_API int ptt_transformer_std_fwd(const float* xyz, const float* features, int B, int n, int d_points, int d_model,
+                            const float* params, float* out, float* attn_or_null, void* workspace,
+                            size_t workspace_bytes, ptt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

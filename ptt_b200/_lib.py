@@ -47,6 +47,10 @@ SIGNATURES = {
     "ptt_transformer_block_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "ptt_transformer_block_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P,
                                           c_size_t, _P]),
+    "ptt_transformer_std_params_floats": (c_size_t, [c_int, c_int]),
+    "ptt_transformer_std_pack_params": (c_int, [c_int, c_int] + [_P] * 11 + [_P, _P]),
+    "ptt_transformer_std_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "ptt_transformer_std_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
 }
 
 _lib = None

@@ -22,6 +22,11 @@ struct PttGemmArgs {
   int ldr = 0;
   float* y = nullptr;
   int ldy = 0;
+  // batched form (tcgen05 path only): `batch` independent problems; x / y / residual advance by their strides (floats)
+  // and the weight image by wimg_bstride (bytes) per batch element
+  int batch = 1;
+  long long x_bstride = 0, y_bstride = 0, res_bstride = 0;
+  size_t wimg_bstride = 0;
 };
 
 // Runs on the tcgen05 path when `wimg` is set and the A operand qualifies (16-byte aligned rows), else on the
@@ -34,7 +39,7 @@ size_t ptt_tc_weight_halves(int K, int Cout);   // size of the fp16 image, in 2-
 // src(c, k) = w[c * ld_c + k * ld_k]: (Cout, K) row-major weight -> ld_c = K, ld_k = 1; transposed (K, ldw) image -> ld_c = 1, ld_k = ldw
 // row_scale (optional, Cout floats): the image holds diag(row_scale) . W
 int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout, int K, void* img, cudaStream_t st,
-                       const float* row_scale = nullptr);
+                       const float* row_scale = nullptr, int batch = 1, long long w_bstride = 0, size_t img_bstride = 0);
 bool ptt_tc_gemm_supported(const PttGemmArgs& a);
 int ptt_tc_gemm_launch(const PttGemmArgs& a, const void* wimg, cudaStream_t st);
 // floats occupied by the tcgen05 image of a (Cout, K) weight

@@ -122,6 +122,10 @@ extern "C" __attribute__((visibility("default"))) void ptt_debug_force_ffma(int 
 
 int ptt_gemm_launch(const PttGemmArgs& a, cudaStream_t st) {
   if (a.R <= 0 || a.N <= 0) return PTT_OK;
+  if (a.batch > 1) {      // batched problems exist on the tensor-core path only
+    const bool ok = a.wimg != nullptr && ptt_tc_gemm_supported(a) && a.x_bstride % 4 == 0;
+    return ok ? ptt_tc_gemm_launch(a, a.wimg, st) : PTT_ERR_UNSUPPORTED;
+  }
   if (a.wimg != nullptr && !g_force_ffma && ptt_tc_gemm_supported(a)) return ptt_tc_gemm_launch(a, a.wimg, st);
   return ptt_gemm_launch_ffma(a, st);
 }

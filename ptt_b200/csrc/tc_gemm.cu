@@ -62,6 +62,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   const int ntile = blockIdx.y;
   const PttGemmArgs& g = p.g;
   const int KB = p.k_blocks;
+  const int bz = blockIdx.z;                                       // batch element
+  const float* gx = g.x + (long long)bz * g.x_bstride;
+  float* gy = g.y + (long long)bz * g.y_bstride;
+  const float* gres = g.residual ? g.residual + (long long)bz * g.res_bstride : nullptr;
+  const uint8_t* gw = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)bz * g.wimg_bstride;
 
   if (tid < TBM) {
     const int r = row0 + tid;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         const int src = s_row[i * 16 + rsub];
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (src >= 0 && k < g.K) {
-          const float* ptr = g.x + (size_t)src * g.ldx + k;
+          const float* ptr = gx + (size_t)src * g.ldx + k;
           if (k + 3 < g.K) {
             v[i] = __ldg(reinterpret_cast<const float4*>(ptr));
           } else {
@@ -135,8 +140,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     tc::tc_fence_after();
     const int r = row0 + warp * 32 + lane;
     const bool row_ok = r < g.R;
-    const bool vec_y = (g.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.y) & 15u) == 0);
-    const bool vec_r = g.residual && (g.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.residual) & 15u) == 0);
+    const bool vec_y = (g.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(gy) & 15u) == 0);
+    const bool vec_r = gres && (g.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(gres) & 15u) == 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       const int col0 = ntile * BN + c0;
@@ -144,8 +149,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       float v[32];
       tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
       if (!row_ok) continue;
-      float* yrow = g.y + (size_t)r * g.ldy + col0;
-      const float* rrow = g.residual ? g.residual + (size_t)r * g.ldr + col0 : nullptr;
+      float* yrow = gy + (size_t)r * g.ldy + col0;
+      const float* rrow = gres ? gres + (size_t)r * g.ldr + col0 : nullptr;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float o[4];
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         tc::mbar_arrive_expect_tx(&full_b[stage], (uint32_t)nsub * 2u * W_BLOCK_BYTES);
         for (int j = 0; j < nsub; ++j) {
           const size_t blk = ((size_t)(ntile * SUB + j) * KB + kb) * 2;
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + blk * W_BLOCK_BYTES;
+          const uint8_t* src = gw + blk * W_BLOCK_BYTES;
           tc::bulk_g2s(b_hi + j * W_BLOCK_BYTES, src, W_BLOCK_BYTES, &full_b[stage]);
           tc::bulk_g2s(b_lo + j * W_BLOCK_BYTES, src + W_BLOCK_BYTES, W_BLOCK_BYTES, &full_b[stage]);
         }
@@ -247,7 +252,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 //   sw128_offset(r, c); rows >= Cout and k >= K are zero.
 //   src(c, k) = w[c * ld_c + k * ld_k]   (so a transposed (K, ldw) image can be the source too)
 __global__ void tc_pack_weight_kernel(const float* __restrict__ w, long long ld_c, long long ld_k, int Cout, int K, int NB,
-                                      int KB, const float* __restrict__ row_scale, __half* __restrict__ img) {
+                                      int KB, const float* __restrict__ row_scale, __half* __restrict__ img,
+                                      long long w_bstride, size_t img_bstride) {
+  w += (long long)blockIdx.y * w_bstride;                                                  // batch element
+  img = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(img) + (size_t)blockIdx.y * img_bstride);
   const long long total = (long long)NB * KB * 64 * 8;   // (block, row, chunk)
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(e & 7);
@@ -279,7 +287,7 @@ int tc_launch(const TcParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  dim3 grid(ceil_div(p.g.R, TBM), ceil_div(p.g.N, BN));
+  dim3 grid(ceil_div(p.g.R, TBM), ceil_div(p.g.N, BN), p.g.batch > 0 ? p.g.batch : 1);
   kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p); PTT_LAUNCHED();
   return ptt_launch_status();
 }
@@ -291,11 +299,12 @@ size_t ptt_tc_weight_halves(int K, int Cout) {
 }
 
 int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout, int K, void* img, cudaStream_t st,
-                       const float* row_scale) {
+                       const float* row_scale, int batch, long long w_bstride, size_t img_bstride) {
   const int NB = ceil_div(Cout, 64), KB = ceil_div(K, 64);
   const long long total = (long long)NB * KB * 512;
-  tc_pack_weight_kernel<<<(unsigned)llmin_((total + 255) / 256, 2048), 256, 0, st>>>(w, ld_c, ld_k, Cout, K, NB, KB,
-                                                                                      row_scale, static_cast<__half*>(img)); PTT_LAUNCHED();
+  dim3 grid((unsigned)llmin_((total + 255) / 256, 2048), batch > 0 ? batch : 1);
+  tc_pack_weight_kernel<<<grid, 256, 0, st>>>(w, ld_c, ld_k, Cout, K, NB, KB, row_scale, static_cast<__half*>(img), w_bstride,
+                                              img_bstride); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
@@ -313,7 +322,7 @@ int ptt_tc_gemm_launch(const PttGemmArgs& a, const void* wimg, cudaStream_t st) 
   // widest tile that still gives the grid at least one CTA per SM (small problems are latency-, not throughput-bound)
   const long long row_tiles = ceil_div(a.R, TBM);
   int bn = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
-  while (bn > 64 && row_tiles * ceil_div(a.N, bn) < 148) bn >>= 1;
+  while (bn > 64 && row_tiles * ceil_div(a.N, bn) * (a.batch > 0 ? a.batch : 1) < 148) bn >>= 1;
   if (bn == 64) return tc_launch<64>(p, st);
   if (bn == 128) return tc_launch<128>(p, st);
   return tc_launch<256>(p, st);

@@ -241,6 +241,49 @@ class TransformerBlockOffset(TransformerBlock):
     VARIANT = 1
 
 
+class TransformerBlockSTD(nn.Module):
+    """Dense n x n dot-product attention (variants.py:12-40); same constructor, forward and state_dict."""
+
+    def __init__(self, d_points, d_model, k, **kwargs):
+        super().__init__()
+        self.fc1 = nn.Linear(d_points, d_model)
+        self.fc2 = nn.Linear(d_model, d_points)
+        self.fc_delta = nn.Sequential(nn.Linear(3, d_model), nn.ReLU(), nn.Linear(d_model, d_model))
+        self.w_qs = nn.Linear(d_model, d_model, bias=False)
+        self.w_ks = nn.Linear(d_model, d_model, bias=False)
+        self.w_vs = nn.Linear(d_model, d_model, bias=False)
+        self.k = k
+        self._packed = None
+
+    def train(self, mode=True):
+        self._packed = None
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def forward(self, xyz, features):
+        if not xyz.is_cuda:
+            raise ops.PttError("ptt_b200.TransformerBlockSTD runs on CUDA only (there is no CPU path)")
+        xyz, features = xyz.contiguous(), features.contiguous()
+        fused = (not self.training) and not (torch.is_grad_enabled() and (xyz.requires_grad or features.requires_grad))
+        if fused:
+            if self._packed is None:
+                self._packed = ops.PackedTransformerSTD({k: v.detach() for k, v in self.state_dict().items()})
+            return ops.transformer_std_fwd(self._packed, xyz, features, want_attn=True)
+        pre = features
+        x = self.fc1(features)
+        q, k, v = self.w_qs(x), self.w_ks(x), self.w_vs(x)
+        attn = F.softmax(q @ k.transpose(1, 2) / math.sqrt(k.size(-1)), dim=-1)
+        res = attn @ (v + self.fc_delta(xyz))
+        return self.fc2(res) + pre, attn
+
+
 def register(install_ext=True):
     """Install the B200 modules into the reference's registries (the reference must be importable
     as `ptt`):  pointnet2_modules.PointnetSAModuleVotes (looked up at construction time by
@@ -255,4 +298,5 @@ def register(install_ext=True):
     pointnet2_modules.PointnetSAModuleVotes = PointnetSAModuleVotes
     transformer_block.__all__["TransformerBlock"] = TransformerBlock
     transformer_block.__all__["TransformerBlockOffset"] = TransformerBlockOffset
+    transformer_block.__all__["TransformerBlockSTD"] = TransformerBlockSTD
     return pointnet2_modules, transformer_block

@@ -369,3 +369,40 @@ def transformer_block_fwd(packed, xyz, features, knn_idx=None, want_attn=False, 
                                           packed.variant, _ptr(packed.params), _ptr(knn_idx), _ptr(out), _ptr(attn),
                                           _ptr(ws), ws.numel() * 4, _stream()), "ptt_transformer_block_fwd")
     return (out, attn) if want_attn else out
+
+
+STD_KEYS = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc_delta.0.weight", "fc_delta.0.bias",
+            "fc_delta.2.weight", "fc_delta.2.bias", "w_qs.weight", "w_ks.weight", "w_vs.weight")
+
+
+class PackedTransformerSTD:
+    """TransformerBlockSTD parameters (variants.py:13-27) packed for ptt_transformer_std_fwd."""
+
+    def __init__(self, sd):
+        ts = [_req(sd[key].contiguous(), _F, sd[key].dim(), key) for key in STD_KEYS]
+        self.d_model, self.d_points = ts[0].shape
+        dev = ts[0].device
+        L = _lib.lib()
+        with _DeviceGuard(dev):
+            self.params = torch.empty(L.ptt_transformer_std_params_floats(self.d_points, self.d_model), dtype=_F, device=dev)
+            check(L.ptt_transformer_std_pack_params(self.d_points, self.d_model, *[_ptr(t) for t in ts], _ptr(self.params),
+                                                    _stream()), "ptt_transformer_std_pack_params")
+            torch.cuda.current_stream().synchronize()
+
+
+def transformer_std_fwd(packed, xyz, features, want_attn=True, workspace=None):
+    """xyz (B,n,3), features (B,n,d_points) -> out (B,n,d_points) [, attn (B,n,n)]."""
+    _req(xyz, _F, 3, "xyz"), _req(features, _F, 3, "features")
+    dev = _same_device(xyz, features)
+    B, n, _ = xyz.shape
+    if tuple(features.shape) != (B, n, packed.d_points):
+        raise PttError("transformer_std_fwd: features must be (B,n,%d)" % packed.d_points)
+    L = _lib.lib()
+    with _DeviceGuard(dev):
+        out = torch.empty(B, n, packed.d_points, dtype=_F, device=dev)
+        attn = torch.empty(B, n, n, dtype=_F, device=dev) if want_attn else None
+        ws_bytes = L.ptt_transformer_std_workspace_bytes(B, n, packed.d_points, packed.d_model)
+        ws = workspace if workspace is not None else _workspace(ws_bytes, dev)
+        check(L.ptt_transformer_std_fwd(_ptr(xyz), _ptr(features), B, n, packed.d_points, packed.d_model, _ptr(packed.params),
+                                        _ptr(out), _ptr(attn), _ptr(ws), ws.numel() * 4, _stream()), "ptt_transformer_std_fwd")
+    return (out, attn) if want_attn else out

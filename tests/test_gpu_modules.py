@@ -45,7 +45,7 @@ def test_sa_module_vs_reference_fixture(golden, name):
     np.testing.assert_allclose(new_feats.cpu().numpy(), gd[name + "/new_features"], **FP_TOL)
 
 
-@pytest.mark.parametrize("name", ["centroid", "box", "small", "offset"])
+@pytest.mark.parametrize("name", ["centroid", "box", "small", "offset", "std"])
 def test_transformer_vs_reference_fixture(golden, name):
     gd = golden("transformer.npz")
     i = list(TR_CASES).index(name)
@@ -257,3 +257,18 @@ def test_host_pipeline_matches_synchronous_api():
     for a, b in zip(got, want):
         for k in a:
             assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("shape", [(3, 128, 256, 512), (2, 100, 32, 64), (1, 1024, 64, 128), (4, 37, 24, 48)])
+def test_transformer_std_vs_port(shape):
+    """Dense n x n attention block (the batched tcgen05 contractions) against the CPU port, incl. N = 1024 tokens,
+    token counts that are not multiples of 64 / 4 and a d_model that is not a multiple of 64."""
+    B, n, dp, dm = shape
+    sd = filled(transformer_state_dict("TransformerBlockSTD", dp, dm), 400 + n)
+    xyz = synth.make_clouds(B, n, 401 + n, "dense", role="template")
+    f = synth.features((B, n, dp), seed=402 + n)
+    want, want_attn = torch_port.transformer_block_std(sd, t(xyz), t(f))
+    packed = ops.PackedTransformerSTD({kk: g(v) for kk, v in sd.items()})
+    got, attn = ops.transformer_std_fwd(packed, g(xyz), g(f))
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), **FP_TOL)
+    np.testing.assert_allclose(attn.cpu().numpy(), want_attn.numpy(), **FP_TOL)
