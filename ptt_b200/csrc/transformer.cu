@@ -23,7 +23,10 @@ struct TrLayout {
   //   qkg   : x -> [Wg0.Wq x | Wg0.Wk x | Wv x]      (replaces the q, k, v projection)
   //   wprime: (Wg0.Wd2) as tcgen05 image, cprime = Wg0.bd2 + bg0
   //   scratch: the three d x d products in fp32 (row-major), kept for inspection
-  size_t qkg, wprime, cprime, scratch, total;
+  //   qkg1  : f -> [Wg0.Wq.W1 f | Wg0.Wk.W1 f | Wv.W1 f] + folded biases: fc1 is linear and x = fc1(f) is only used through
+  //           q, k, v (variants.py:152-153), so the token projection is ONE d_points -> 3 d_model contraction
+  //   scratch2: temporaries of that fold (two dm x dp products, two dm vectors)
+  size_t qkg, wprime, cprime, scratch, qkg1, scratch2, total;
 };
 
 bool tr_layout(int dp, int dm, TrLayout* L) {
@@ -47,6 +50,8 @@ bool tr_layout(int dp, int dm, TrLayout* L) {
   L->wprime = off; off += ptt_tc_weight_floats(dm, dm);
   L->cprime = off; off += round_up(dm, 4);
   L->scratch = off; off += (size_t)3 * dm * dm;
+  L->qkg1 = take(dp, 3 * round_up(dm, 4));
+  L->scratch2 = off; off += (size_t)2 * dm * round_up(dp, 4) + 2 * round_up(dm, 4);
   L->total = off;
   return true;
 }
@@ -60,6 +65,17 @@ __global__ void tr_cprime_kernel(const float* __restrict__ wg0, const float* __r
   if (bd2)
     for (int m = 0; m < dm; ++m) acc = fmaf(wg0[(size_t)c * dm + m], bd2[m], acc);
   cprime[c] = acc;
+}
+
+// out[c] = sum_m w[c * ldw + m] * v[m]   (v == nullptr: out = 0)
+__global__ void tr_matvec_kernel(const float* __restrict__ w, int ldw, const float* __restrict__ v, int rows, int K,
+                                 float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= rows) return;
+  float acc = 0.f;
+  if (v)
+    for (int m = 0; m < K; ++m) acc = fmaf(w[(size_t)c * ldw + m], v[m], acc);
+  out[c] = acc;
 }
 
 // h[(b,i,j), c] = relu(Wd0[c,:] . (xyz_i - xyz_knn(i,j)) + bd0[c])      delta0 image: 3 rows wt + bias row
@@ -216,6 +232,25 @@ extern "C" int ptt_transformer_pack_params(int d_points, int d_model, const floa
     if ((rc = ptt_linear_pack_cols(sc + (size_t)2 * dm * dm, nullptr, dm, dm, 3 * ld, ld, params + L.qkg, st))) return rc;
     if ((rc = ptt_linear_pack_cols(wv, nullptr, dm, dm, 3 * ld, 2 * ld, params + L.qkg, st))) return rc;
     if ((rc = tc_pack(L.qkg, dm, 3 * ld))) return rc;
+    // fold fc1 into the token projection: P = W . W1 (dm x dp), bias = W . b1, for W in {Wg0.Wq, Wg0.Wk, Wv}
+    const int ldp = round_up(dp, 4);
+    float* T = params + L.scratch2;                 // fc1_w copied to 16-byte aligned rows of ldp floats (any d_points)
+    float* P = T + (size_t)dm * ldp;
+    float* bv = P + (size_t)dm * ldp;
+    e = cudaMemcpy2DAsync(T, (size_t)ldp * sizeof(float), fc1_w, (size_t)dp * sizeof(float), (size_t)dp * sizeof(float), dm,
+                          cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+    const float* mats[3] = {sc + (size_t)dm * dm, sc + (size_t)2 * dm * dm, wv};          // Wg0.Wq, Wg0.Wk, Wv (dm x dm, row-major)
+    for (int i = 0; i < 3; ++i) {
+      PttGemmArgs g;                                // P (dm x dp, row stride dp) = mats[i] (dm x dm) . fc1_w (dm x dp)
+      g.x = mats[i]; g.ldx = dm; g.R = dm; g.K = dm;
+      g.wt = T; g.ldw = ldp; g.N = dp;
+      g.y = P; g.ldy = dp;
+      if ((rc = ptt_gemm_launch_ffma(g, st))) return rc;
+      tr_matvec_kernel<<<ceil_div(dm, 128), 128, 0, st>>>(mats[i], dm, fc1_b, dm, dm, bv); PTT_LAUNCHED();
+      if ((rc = ptt_linear_pack_cols(P, bv, dp, dm, 3 * ld, i * ld, params + L.qkg1, st))) return rc;
+    }
+    if ((rc = tc_pack(L.qkg1, dp, 3 * ld))) return rc;
   }
   return ptt_launch_status();
 }
@@ -274,9 +309,15 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
   };
 
   const bool fused = tr_fused_supported(n, k, dm);
-  if ((rc = linear(features, dp, tokens, dp, L.fc1, dm, ld, true, 0, nullptr, 0, x, ld))) return rc;
-  // fused path: [Wg0.Wq x | Wg0.Wk x | Wv x]; generic path: [q | k | v]
-  if ((rc = linear(x, ld, tokens, dm, fused ? L.qkg : L.qkv, 3 * ld, 3 * ld, false, 0, nullptr, 0, qkv, ldq))) return rc;
+  // fused path, plain variant: fc1 is folded into the projection (x itself is never needed); Offset variant: x is kept
+  // for fc2(x - res).  fused: [Wg0.Wq x | Wg0.Wk x | Wv x]; generic path: [q | k | v]
+  const bool folded = fused && variant == 0;
+  if (folded) {
+    if ((rc = linear(features, dp, tokens, dp, L.qkg1, 3 * ld, 3 * ld, true, 0, nullptr, 0, qkv, ldq))) return rc;
+  } else {
+    if ((rc = linear(features, dp, tokens, dp, L.fc1, dm, ld, true, 0, nullptr, 0, x, ld))) return rc;
+    if ((rc = linear(x, ld, tokens, dm, fused ? L.qkg : L.qkv, 3 * ld, 3 * ld, false, 0, nullptr, 0, qkv, ldq))) return rc;
+  }
 
   if (fused) {
     // ---- pair-row passes on the tensor cores with generated A operands and fused reductions (tr_fused.cu)
