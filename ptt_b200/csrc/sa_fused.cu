@@ -25,21 +25,27 @@ namespace {
 
 constexpr int SF_THREADS = 576;            // 8 epilogue + 8 producer warps + loader + MMA
 constexpr int SF_TM = 128;
-constexpr int SF_NS = 3;                       // ring stages
+constexpr int SF_NS = 3;                       // weight ring stages
 constexpr uint32_t SF_STAGE_BYTES = 32768;     // one weight item: <=128 rows x 64 k, hi + lo
 constexpr uint32_t SF_KBLOCK_BYTES = 32768;    // one activation k-block: 128 rows x 64 k, hi (16 KB) + lo (16 KB)
 
+// H1 and H2 live in RINGS of k-block slots (NRA / NRB of them) handed over one k-block at a time: producers -> layer 2 and
+// epilogue -> layer 3.  Up to 128-wide hidden layers a ring holds the whole activation (slot == k-block); at 256 it holds
+// two k-blocks, which is what lets the (256, 256, 256) stack of the box head fit next to the weight ring.
 template <int D1, int D2, int D3>
 struct SfCfg {
   static constexpr int KB1 = D1 / 64, KB2 = D2 / 64;
+  static constexpr int NRA = KB1 < 2 ? KB1 : 2, NRB = KB2 < 2 ? KB2 : 2;
   static constexpr int NI2 = D2 < 128 ? D2 : 128, NI3 = D3 < 128 ? D3 : 128;   // MMA N / rows per weight item
   static constexpr int ITEMS2 = D2 / NI2, ITEMS3 = D3 / NI3;                   // items per k-block
-  static constexpr uint32_t HA_BYTES = KB1 * SF_KBLOCK_BYTES;
-  static constexpr uint32_t HB_BYTES = KB2 * SF_KBLOCK_BYTES;
+  static constexpr bool SH2_SMEM = D2 < 256;                                    // shift2 staged in shared memory when it fits
+  static constexpr uint32_t HA_BYTES = NRA * SF_KBLOCK_BYTES;
+  static constexpr uint32_t HB_BYTES = NRB * SF_KBLOCK_BYTES;
   static constexpr uint32_t RING_BYTES = SF_NS * SF_STAGE_BYTES;
-  static constexpr uint32_t CTRL_BYTES = 256 + 128 * 16 + D2 * 4;
-  static constexpr uint32_t SMEM_BYTES = HA_BYTES + HB_BYTES + RING_BYTES + CTRL_BYTES;   // 232,192 B at (128,128,256): 256 B under the 227 KB limit
-  static constexpr uint32_t D2_COL = 0, D3_COL = 128, TMEM_COLS = 512;
+  static constexpr uint32_t CTRL_BYTES = 256 + 128 * 16 + (SH2_SMEM ? D2 * 4 : 0);
+  static constexpr uint32_t SMEM_BYTES = HA_BYTES + HB_BYTES + RING_BYTES + CTRL_BYTES;   // 231,680 B at (256,256,256); limit 232,448
+  static constexpr uint32_t D2_COL = 0, D3_COL = D2 < 128 ? 128 : D2, TMEM_COLS = 512;
+  static_assert(D3_COL + D3 <= 512, "accumulators exceed TMEM");
 };
 
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -71,28 +77,35 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
   uint8_t* ctrl = ring + Cfg::RING_BYTES;
   uint64_t* full_b = reinterpret_cast<uint64_t*>(ctrl);   // [SF_NS]
   uint64_t* empty = full_b + SF_NS;                        // [SF_NS]
-  uint64_t* ha_full = empty + SF_NS;
-  uint64_t* ha_free = ha_full + 1;
-  uint64_t* d2_full = ha_free + 1;
-  uint64_t* hb_full = d2_full + 1;                         // [KB2]: H2 is handed over k-block by k-block
-  uint64_t* d3_full = hb_full + Cfg::KB2;
+  uint64_t* ha_full = empty + SF_NS;                       // [NRA] producers -> MMA
+  uint64_t* ha_free = ha_full + Cfg::NRA;                  // [NRA] MMA -> producers
+  uint64_t* hb_full = ha_free + Cfg::NRA;                  // [NRB] epilogue -> MMA
+  uint64_t* hb_free = hb_full + Cfg::NRB;                  // [NRB] MMA -> epilogue
+  uint64_t* d2_full = hb_free + Cfg::NRB;
+  uint64_t* d3_full = d2_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d3_full + 1);
   float4* s_info = reinterpret_cast<float4*>(ctrl + 256);                 // [128] {rel.xyz, point row as int bits}
   float* s_sh2 = reinterpret_cast<float*>(ctrl + 256 + 128 * 16);         // [D2] (shift3 stays in global: E3 is off the critical path)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((tc::smem_u32(smem) & 1023u) != 0) __trap();          // the UMMA tiles need 1024-byte alignment
-  for (int c = tid; c < D2; c += SF_THREADS) s_sh2[c] = __ldg(a.shift2 + c);
+  if (Cfg::SH2_SMEM)
+    for (int c = tid; c < D2; c += SF_THREADS) s_sh2[c] = __ldg(a.shift2 + c);
 
   if (tid == 0) {
     for (int s = 0; s < SF_NS; ++s) {
       tc::mbar_init(&full_b[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
-    tc::mbar_init(ha_full, 256);
-    tc::mbar_init(ha_free, 1);
+    for (int s = 0; s < Cfg::NRA; ++s) {
+      tc::mbar_init(&ha_full[s], 256);
+      tc::mbar_init(&ha_free[s], 1);
+    }
+    for (int s = 0; s < Cfg::NRB; ++s) {
+      tc::mbar_init(&hb_full[s], 256);
+      tc::mbar_init(&hb_free[s], 1);
+    }
     tc::mbar_init(d2_full, 1);
-    for (int s = 0; s < Cfg::KB2; ++s) tc::mbar_init(&hb_full[s], 256);
     tc::mbar_init(d3_full, 1);
     tc::mbar_init_fence();
   }
@@ -110,10 +123,12 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const unsigned gmask = ns >= 32 ? 0xffffffffu : (((1u << ns) - 1u) << (lane & ~(ns - 1)));
     int it = 0;
+    int sb = 0;                 // H2 ring slot
+    uint32_t pb = 0;            // its phase
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t par = it & 1;
       const bool erec = a.dbg != nullptr && blockIdx.x == 0 && tid == 0 && it < 30;
-      // ---- E2: D2 -> H2 (HB), one 64-column k-block at a time so that layer 3 can start on the first one
+      // ---- E2: D2 -> H2, one 64-column k-block at a time so that layer 3 can start on the first one
       tc::mbar_wait(d2_full, par);
       tc::tc_fence_after();
       if (erec) a.dbg[1000 + it * 4 + 0] = clock64();
@@ -122,12 +137,19 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         const int c0 = kb * 64 + half * 32;
         float v[32];
         tc::tmem_ld32(lane_addr + Cfg::D2_COL + (uint32_t)c0, v);
-        uint8_t* blk = HB + kb * SF_KBLOCK_BYTES;
+        tc::mbar_wait(&hb_free[sb], pb ^ 1);            // layer 3 has consumed the k-block that used this slot
+        uint8_t* blk = HB + sb * SF_KBLOCK_BYTES;
         const int chunk0 = half * 4;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const float4 s0 = *reinterpret_cast<const float4*>(s_sh2 + c0 + ch * 8);
-          const float4 s1 = *reinterpret_cast<const float4*>(s_sh2 + c0 + ch * 8 + 4);
+          float4 s0, s1;
+          if (Cfg::SH2_SMEM) {
+            s0 = *reinterpret_cast<const float4*>(s_sh2 + c0 + ch * 8);
+            s1 = *reinterpret_cast<const float4*>(s_sh2 + c0 + ch * 8 + 4);
+          } else {
+            s0 = __ldg(reinterpret_cast<const float4*>(a.shift2 + c0 + ch * 8));
+            s1 = __ldg(reinterpret_cast<const float4*>(a.shift2 + c0 + ch * 8 + 4));
+          }
           const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
           float h[8];
 #pragma unroll
@@ -143,7 +165,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         }
         tc::tc_fence_before();
         tc::fence_proxy_async_smem();
-        tc::mbar_arrive(&hb_full[kb]);
+        tc::mbar_arrive(&hb_full[sb]);
+        if (++sb == Cfg::NRB) { sb = 0; pb ^= 1; }
       }
       if (erec) a.dbg[1000 + it * 4 + 1] = clock64();
       // ---- E3: D3 -> max over each centre's rows -> out
@@ -179,19 +202,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
   } else if (warp < 16) {
     // =================================================================== producers: layer 1 on CUDA cores
     const int pt = tid - 256;            // 0..255
-    const int q = pt & 15;               // float4 column (and q + 16 when D1 == 128)
+    const int q = pt & 15;               // float4 column of the k-block
     const int rsub = pt >> 4;            // 0..15
-    constexpr int NQ = D1 / 64;          // float4 columns per thread
-    float wx[NQ][3][4], g0[NQ][4];
-#pragma unroll
-    for (int h = 0; h < NQ; ++h)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = (q + 16 * h) * 4 + u;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) wx[h][d][u] = __ldg(a.wx + d * D1 + c);
-        g0[h][u] = a.gprime ? 0.f : __ldg(a.shift1 + c);
-      }
     // Per-row neighbour info is software-pipelined: the dependent global loads (ball-query index -> point) of tile
     // t+1 are issued before H1 of tile t is written, so their latency never sits on the producers' critical path.
     auto row_index = [&](int tile) -> int {          // ball-query result of this thread's row, -1 beyond the end
@@ -212,10 +224,27 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       }
       return info;
     };
+    // layer-1 xyz weights of this thread's channels: kept in registers for up to two k-blocks, re-read (L1) beyond
+    constexpr bool HOIST = Cfg::KB1 <= 2;
+    constexpr int HK = HOIST ? Cfg::KB1 : 1;
+    float wxr[HK][3][4], g0r[HK][4];
+    if (HOIST) {
+#pragma unroll
+      for (int h = 0; h < HK; ++h)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = h * 64 + q * 4 + u;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) wxr[h][d][u] = __ldg(a.wx + d * D1 + c);
+          g0r[h][u] = a.gprime ? 0.f : __ldg(a.shift1 + c);
+        }
+    }
     const int stride = gridDim.x;
     int idx_next = row_index(blockIdx.x + stride);              // index for tile t+1
     float4 info_cur = row_info(blockIdx.x, row_index(blockIdx.x));
     int it = 0;
+    int sa = 0;                 // H1 ring slot
+    uint32_t pa = 0;            // its phase
     for (int tile = blockIdx.x; tile < num_tiles; tile += stride, ++it) {
       producer_bar();                                   // everyone is done reading s_info of the previous tile
       if (pt < SF_TM) s_info[pt] = info_cur;
@@ -225,37 +254,46 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       const int idx_nn = row_index(tile + 2 * stride);
       const bool prec = a.dbg != nullptr && blockIdx.x == 0 && pt == 0 && it < 30;
       if (prec) a.dbg[2000 + it * 3 + 0] = clock64();
-      tc::mbar_wait(ha_free, (uint32_t)(it & 1) ^ 1u);  // GEMM2 of the previous tile has consumed HA
-      if (prec) a.dbg[2000 + it * 3 + 1] = clock64();
-#pragma unroll 4
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 16 + rsub;
-        const float4 info = s_info[r];
-        const int src = __float_as_int(info.w);
 #pragma unroll
-        for (int h = 0; h < NQ; ++h) {
-          float4 g = make_float4(g0[h][0], g0[h][1], g0[h][2], g0[h][3]);
-          if (a.gprime != nullptr && src >= 0) g = __ldg(reinterpret_cast<const float4*>(a.gprime + (size_t)src * D1 + (q + 16 * h) * 4));
+      for (int h = 0; h < Cfg::KB1; ++h) {
+        const int c = h * 64 + q * 4;                   // this thread's 4 channels of k-block h
+        float wx[3][4], g0[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) wx[d][u] = HOIST ? wxr[h < HK ? h : 0][d][u] : __ldg(a.wx + d * D1 + c + u);
+          g0[u] = HOIST ? g0r[h < HK ? h : 0][u] : (a.gprime ? 0.f : __ldg(a.shift1 + c + u));
+        }
+        tc::mbar_wait(&ha_free[sa], pa ^ 1);            // layer 2 has consumed the k-block that used this slot
+        if (prec && h == 0) a.dbg[2000 + it * 3 + 1] = clock64();
+        uint8_t* blk = HA + sa * SF_KBLOCK_BYTES;
+#pragma unroll 4
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 16 + rsub;
+          const float4 info = s_info[r];
+          const int src = __float_as_int(info.w);
+          float4 g = make_float4(g0[0], g0[1], g0[2], g0[3]);
+          if (a.gprime != nullptr && src >= 0) g = __ldg(reinterpret_cast<const float4*>(a.gprime + (size_t)src * D1 + c));
           float y[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            float t = fmaf(wx[h][0][u], info.x, y[u]);
-            t = fmaf(wx[h][1][u], info.y, t);
-            t = fmaf(wx[h][2][u], info.z, t);
+            float t = fmaf(wx[0][u], info.x, y[u]);
+            t = fmaf(wx[1][u], info.y, t);
+            t = fmaf(wx[2][u], info.z, t);
             y[u] = src >= 0 ? fmaxf(t, 0.f) : 0.f;
           }
           uint2 hi, lo;
           tc::split_f16x2(y[0], y[1], hi.x, lo.x);
           tc::split_f16x2(y[2], y[3], hi.y, lo.y);
-          uint8_t* blk = HA + h * SF_KBLOCK_BYTES;
           const uint32_t off = tc::sw128_offset(r, q >> 1) + ((q & 1) << 3);
           *reinterpret_cast<uint2*>(blk + off) = hi;
           *reinterpret_cast<uint2*>(blk + 16384 + off) = lo;
         }
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&ha_full[sa]);
+        if (++sa == Cfg::NRA) { sa = 0; pa ^= 1; }
       }
-      tc::fence_proxy_async_smem();
       if (prec) a.dbg[2000 + it * 3 + 2] = clock64();
-      tc::mbar_arrive(ha_full);
       info_cur = info_nxt;
       idx_next = idx_nn;
     }
@@ -288,26 +326,26 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       constexpr uint32_t IDESC3 = tc::idesc_f16<false>(SF_TM, Cfg::NI3);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       const uint32_t ha_addr = tc::smem_u32(HA), hb_addr = tc::smem_u32(HB), ring_addr = tc::smem_u32(ring);
       const bool rec = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
       int nrec = 0;
       auto stamp = [&](int tag) { if (rec && nrec < 300) { a.dbg[2 * nrec] = tag; a.dbg[2 * nrec + 1] = clock64(); ++nrec; } };
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t par = it & 1;
-        // ---- layer 2: D2 = H1 . W2'^T
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // ---- layer 2: D2 = H1 . W2'^T, k-block by k-block as the producers hand H1 over
         stamp(1);
-        tc::mbar_wait(ha_full, par);
-        tc::tc_fence_after();
-        stamp(2);
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB1; ++kb) {
+          tc::mbar_wait(&ha_full[sa], pa);
+          tc::tc_fence_after();
+          if (kb == 0) stamp(2);
 #pragma unroll 1
           for (int ni = 0; ni < Cfg::ITEMS2; ++ni) {
             tc::mbar_wait(&full_b[stage], phase);
             tc::tc_fence_after();
-            const uint64_t da_hi = tc::smem_desc_sw128(ha_addr + kb * SF_KBLOCK_BYTES);
-            const uint64_t da_lo = tc::smem_desc_sw128(ha_addr + kb * SF_KBLOCK_BYTES + 16384);
+            const uint64_t da_hi = tc::smem_desc_sw128(ha_addr + sa * SF_KBLOCK_BYTES);
+            const uint64_t da_lo = tc::smem_desc_sw128(ha_addr + sa * SF_KBLOCK_BYTES + 16384);
             const uint64_t db_hi = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES);
             const uint64_t db_lo = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES + Cfg::NI2 * 128);
             const uint32_t d = tmem_base + Cfg::D2_COL + ni * Cfg::NI2;
@@ -321,22 +359,23 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
             tc::mma_commit_w(&empty[stage]);
             if (++stage == SF_NS) { stage = 0; phase ^= 1; }
           }
+          tc::mma_commit_w(&ha_free[sa]);
+          if (++sa == Cfg::NRA) { sa = 0; pa ^= 1; }
         }
-        tc::mma_commit_w(ha_free);
         tc::mma_commit_w(d2_full);
         stamp(3);
         // ---- layer 3: D3 = H2 . W3'^T, k-block by k-block as the epilogue hands H2 over
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB2; ++kb) {
-          tc::mbar_wait(&hb_full[kb], par);
+          tc::mbar_wait(&hb_full[sb], pb);
           tc::tc_fence_after();
           if (kb == 0) stamp(4);
 #pragma unroll 1
           for (int ni = 0; ni < Cfg::ITEMS3; ++ni) {
             tc::mbar_wait(&full_b[stage], phase);
             tc::tc_fence_after();
-            const uint64_t da_hi = tc::smem_desc_sw128(hb_addr + kb * SF_KBLOCK_BYTES);
-            const uint64_t da_lo = tc::smem_desc_sw128(hb_addr + kb * SF_KBLOCK_BYTES + 16384);
+            const uint64_t da_hi = tc::smem_desc_sw128(hb_addr + sb * SF_KBLOCK_BYTES);
+            const uint64_t da_lo = tc::smem_desc_sw128(hb_addr + sb * SF_KBLOCK_BYTES + 16384);
             const uint64_t db_hi = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES);
             const uint64_t db_lo = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES + Cfg::NI3 * 128);
             const uint32_t d = tmem_base + Cfg::D3_COL + ni * Cfg::NI3;
@@ -350,6 +389,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
             tc::mma_commit_w(&empty[stage]);
             if (++stage == SF_NS) { stage = 0; phase ^= 1; }
           }
+          tc::mma_commit_w(&hb_free[sb]);
+          if (++sb == Cfg::NRB) { sb = 0; pb ^= 1; }
         }
         tc::mma_commit_w(d3_full);
         stamp(5);
@@ -391,7 +432,8 @@ long long* g_sa_dbg = nullptr;   // tuning hook: timeline buffer picked up by th
 extern "C" __attribute__((visibility("default"))) void ptt_debug_sa_timeline(long long* buf) { g_sa_dbg = buf; }
 
 bool sa_fused_supported(int d1, int d2, int d3, int ns) {
-  const bool dims = (d1 == 64 && d2 == 64 && d3 == 128) || (d1 == 128 && d2 == 128 && d3 == 256);
+  const bool dims = (d1 == 64 && d2 == 64 && d3 == 128) || (d1 == 128 && d2 == 128 && d3 == 256) ||
+                    (d1 == 256 && d2 == 256 && d3 == 256);
   const bool group = ns >= 1 && ns <= 32 && (ns & (ns - 1)) == 0;
   return dims && group;
 }
@@ -402,5 +444,6 @@ int sa_fused_launch(const SaFusedArgs& a_in, int d1, int d2, int d3, cudaStream_
   if (a.rows <= 0) return PTT_OK;
   if (d1 == 64 && d2 == 64 && d3 == 128) return sf_launch<64, 64, 128>(a, st);
   if (d1 == 128 && d2 == 128 && d3 == 256) return sf_launch<128, 128, 256>(a, st);
+  if (d1 == 256 && d2 == 256 && d3 == 256) return sf_launch<256, 256, 256>(a, st);
   return PTT_ERR_UNSUPPORTED;
 }

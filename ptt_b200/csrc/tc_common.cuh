@@ -239,6 +239,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 256-bit read-only global load: one full 32-byte sector per lane (address 32-byte aligned)
+__device__ __forceinline__ void ld_global_nc_v8(const float* p, float (&o)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
+               : "l"(p));
+}
+
 // 2^x, one MUFU.EX2 (flush-to-zero: no denormal range fix-up around it)
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

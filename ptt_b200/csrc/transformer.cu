@@ -275,7 +275,7 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
   TrWorkspace W;
   tr_workspace(B, n, k, L, &W);
   if (workspace == nullptr || workspace_bytes < W.total * sizeof(float)) return PTT_ERR_WORKSPACE;
-  if ((reinterpret_cast<uintptr_t>(workspace) & 15u) != 0) return PTT_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 31u) != 0) return PTT_ERR_WORKSPACE;   // 256-bit loads / stores of workspace rows
   cudaStream_t st = as_stream(stream);
   float* ws = static_cast<float*>(workspace);
   const int dp = d_points, dm = d_model, ld = W.ld, ldq = W.ldq;

@@ -166,7 +166,14 @@ class HotPath:
             ws = self._workspace("centroid.transformer", self.centroid_tr.workspace_bytes(s_xyz.shape[0], s_xyz.shape[1]))
             with self._Stage(self, "centroid.transformer"):
                 cen = ops.transformer_block_fwd(self.centroid_tr, s_xyz, s_feat_pm, workspace=ws)
-            votes_pm = torch.cat([torch.full_like(cen[:, :, :1], 0.5), cen], dim=2)     # glue: [score | feats]
+            # glue: [score | feats], rows padded to a multiple of 4 floats so that the per-point layer-1 contraction of
+            # the box SA reads 16-byte aligned rows (tensor-core path); the padding columns are never read (C = 257)
+            C = cen.shape[2] + 1
+            votes_pm = torch.empty(cen.shape[0], cen.shape[1], (C + 3) // 4 * 4, dtype=cen.dtype, device=cen.device)
+            votes_pm[:, :, 0] = 0.5
+            votes_pm[:, :, 1:C] = cen
+            if votes_pm.shape[2] > C:
+                votes_pm[:, :, C:] = 0.0
             b_xyz, b_feat_pm, b_feat, _ = self._sa_layer(self.box_sa, s_xyz, votes_pm, c["box_npoint"], c["box_radius"],
                                                          c["box_nsample"], "fps", want_cm=True, tag="box.sa")
             ws = self._workspace("box.transformer", self.box_tr.workspace_bytes(b_xyz.shape[0], b_xyz.shape[1]))
