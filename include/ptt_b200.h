@@ -137,6 +137,22 @@ PTT_API int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, const 
                    void* workspace, size_t workspace_bytes, ptt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * N1  CosineSimAug fusion (similarity_modules/p2b_xcoor.py:25-43)
+ *
+ *   search_feats (B,n2,lds>=f), template_feats (B,n1,ldt>=f) point-major, template_xyz (B,n1,3)
+ *   -> out_pm (B,n2,ld_out): max over the n1 templates of SharedMLP([cos(t,s) | xyz_t | feats_t]).
+ *   The 1x1 Conv1d stack that follows (p2b_xcoor.py:44) is two ptt_linear_fwd calls.
+ *   params: ptt_sa_pack_params image for C = 3 + f whose layer-0 weight has its (1 + 3 + f) reference input
+ *   columns re-ordered to [w_sim, 0, 0 | W0[:, 1:]] (i.e. dims[0] = f + 6): the fusion is a set-abstraction
+ *   layer over the templates with the similarity as the only pair-dependent input (see csrc/sa_mlp.cu).
+ * ------------------------------------------------------------------------------------------- */
+PTT_API size_t ptt_cosine_fusion_workspace_bytes(int B, int n1, int n2, int f, int n_layers, const int* h_dims);
+PTT_API int ptt_cosine_fusion_fwd(const float* search_feats, int lds, const float* template_feats, int ldt,
+                          const float* template_xyz, int B, int n1, int n2, int f, int n_layers,
+                          const int* h_dims, const float* params, float* out_pm, int ld_out, void* workspace,
+                          size_t workspace_bytes, ptt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a9  TransformerBlock.forward (kNN vector attention)           transformer_block/variants.py:149-165
  *
  *   knn: xyz (B,n,3) -> knn_idx (B,n,k): the k nearest (self included) by the fp32 squared distance

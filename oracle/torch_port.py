@@ -182,3 +182,85 @@ def hot_path_frame(sd, search, template, cfg=None):
     return {"search_seeds": s_xyz, "search_feats": s_feat, "search_inds": s_inds,
             "template_seeds": t_xyz, "template_feats": t_feat, "template_inds": t_inds,
             "centroid_feats": cen, "box_centers": b_xyz, "box_sa_feats": b_feat, "box_feats": box}
+
+
+# ----------------------------------------------------------------------------------------------
+# the modules between the hot stages, so that the checker covers the whole tracker forward.
+# ----------------------------------------------------------------------------------------------
+def seq_conv1d(sd, x, training=False, eps=1e-5):
+    """pytorch_utils.Seq of Conv1d layers (pytorch_utils.py:270-300; keys {i}.conv.weight (Cout,Cin,1),
+    {i}.conv.bias, {i}.normlayer.bn.*).  ReLU after every layer but the last (the heads and the similarity
+    module all end with activation=None: centroids_voting_head.py:14-25, box_voting_head.py:24-29,
+    p2b_xcoor.py:20-24).  x (B,C,N)."""
+    n = 0
+    while "%d.conv.weight" % n in sd:
+        n += 1
+    for i in range(n):
+        p = "%d." % i
+        x = F.conv1d(x, sd[p + "conv.weight"], sd.get(p + "conv.bias"))
+        if p + "normlayer.bn.weight" in sd:
+            x = F.batch_norm(x, sd[p + "normlayer.bn.running_mean"], sd[p + "normlayer.bn.running_var"],
+                             sd[p + "normlayer.bn.weight"], sd[p + "normlayer.bn.bias"], training=training, eps=eps)
+        if i < n - 1:
+            x = F.relu(x)
+    return x
+
+
+def cosine_sim_aug(sd, search_feats, template_feats, template_xyz):
+    """CosineSimAug.forward (similarity_modules/p2b_xcoor.py:25-46).  search_feats (B,f,n2), template_feats (B,f,n1),
+    template_xyz (B,n1,3) -> cosine_feats (B,256,n2)."""
+    b, f, n2 = search_feats.shape
+    n1 = template_feats.shape[-1]
+    sim = F.cosine_similarity(template_feats.unsqueeze(-1).expand(b, f, n1, n2),
+                              search_feats.unsqueeze(2).expand(b, f, n1, n2), dim=1)                # :36-37
+    xyz_ = template_xyz.transpose(1, 2).contiguous().unsqueeze(-1).expand(b, 3, n1, n2)             # :38
+    fusion = torch.cat((sim.unsqueeze(1), xyz_), dim=1)                                             # :39
+    fusion = torch.cat((fusion, template_feats.unsqueeze(-1).expand(b, f, n1, n2)), dim=1)          # :40
+    fusion = shared_mlp(_sub(sd, "mlp."), fusion)                                                    # :41
+    fusion = fusion.max(dim=2)[0]                                                                    # :42-43
+    return seq_conv1d(_sub(sd, "conv."), fusion)                                                     # :44
+
+
+def centroid_voting_head(sd, search_seeds, cosine_feats, k):
+    """CentroidVotingHead.forward (voting_heads/centroids_voting_head.py:66-100), CLS_USE_SEARCH_XYZ False.
+    -> pred_centroids_cls (B,n), pred_centroids_votes (B,n,3), votes_feats (B,257,n), trans_feat (B,n,256)."""
+    xyz_cm = search_seeds.transpose(1, 2).contiguous()
+    trans, _ = transformer_block(_sub(sd, "transformer_block."), search_seeds, cosine_feats.transpose(1, 2).contiguous(), k)
+    fusion = trans.transpose(1, 2).contiguous()
+    cls_out = seq_conv1d(_sub(sd, "cla_layer."), fusion).squeeze(1)                                  # :87
+    score = cls_out.sigmoid()
+    voting_input = torch.cat((xyz_cm, fusion), dim=1)                                                # :92
+    voting_results = voting_input + seq_conv1d(_sub(sd, "vote_layer."), voting_input)               # :93-95
+    votes = voting_results[:, 0:3, :].transpose(1, 2).contiguous()
+    votes_feats = torch.cat((score.unsqueeze(1), voting_results[:, 3:, :]), dim=1)                   # :100
+    return cls_out, votes, votes_feats, trans
+
+
+def box_voting_head(sd, votes, votes_feats, c):
+    """BoxVotingHead.forward, eval (voting_heads/box_voting_head.py:70-95)."""
+    b_xyz, b_feat, _ = sa_module_votes(_sub(sd, "vote_aggregation."), votes, votes_feats, c["box_npoint"],
+                                       c["box_radius"], c["box_nsample"], "fps", True, True)
+    box, _ = transformer_block(_sub(sd, "transformer_block."), b_xyz, b_feat.transpose(1, 2).contiguous(), c["knn"])
+    off = seq_conv1d(_sub(sd, "refine_layer."), box.transpose(1, 2).contiguous())                    # :88
+    est = torch.cat((off[:, 0:3, :] + b_xyz.transpose(1, 2).contiguous(), off[:, 3:, :]), dim=1)     # :90-91
+    return b_xyz, est.transpose(1, 2).contiguous(), b_feat, box
+
+
+def full_model_frame(sd, search, template, cfg=None):
+    """The whole PTT tracker forward in eval mode (trackers/ptt.py:45-46 over the module list of ptt.yaml):
+    backbone -> CosineSimAug -> CentroidVotingHead -> BoxVotingHead.  ptt_b200.hotpath.HotPath.forward_full is the
+    product twin."""
+    c = dict(npoints_search=(512, 256, 128), npoints_template=(256, 128, 64), radii=(0.3, 0.5, 0.7),
+             nsamples=(32, 32, 32), knn=16, box_npoint=64, box_radius=0.3, box_nsample=16)
+    c.update(cfg or {})
+    bb = _sub(sd, "backbone_3d.")
+    s_xyz, s_feat, s_inds = backbone_branch(bb, search, c["npoints_search"], c["radii"], c["nsamples"])
+    t_xyz, t_feat, t_inds = backbone_branch(bb, template, c["npoints_template"], c["radii"], c["nsamples"])
+    cos = cosine_sim_aug(_sub(sd, "similarity_module."), s_feat, t_feat, t_xyz)
+    cls_out, votes, votes_feats, cen = centroid_voting_head(_sub(sd, "centroid_voting_head."), s_xyz, cos, c["knn"])
+    b_xyz, box_data, b_feat, box = box_voting_head(_sub(sd, "box_voting_head."), votes, votes_feats, c)
+    return {"search_seeds": s_xyz, "search_feats": s_feat, "search_inds": s_inds,
+            "template_seeds": t_xyz, "template_feats": t_feat, "template_inds": t_inds,
+            "cosine_feats": cos, "centroid_feats": cen, "pred_centroids_cls": cls_out, "pred_centroids_votes": votes,
+            "votes_feats": votes_feats, "pred_box_center": b_xyz, "box_sa_feats": b_feat, "box_feats": box,
+            "pred_box_data": box_data}

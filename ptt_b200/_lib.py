@@ -38,6 +38,9 @@ SIGNATURES = {
     "ptt_sa_mlp_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, _IP]),
     "ptt_sa_mlp_fwd": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                _IP, _P, _P, c_int, _P, _P, c_size_t, _P]),
+    "ptt_cosine_fusion_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, _IP]),
+    "ptt_cosine_fusion_fwd": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _IP, _P, _P, c_int, _P,
+                                      c_size_t, _P]),
     "ptt_knn": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "ptt_linear_params_floats": (c_size_t, [c_int, c_int]),
     "ptt_linear_pack": (c_int, [_P, _P, c_int, c_int, _P, _P]),

@@ -192,8 +192,15 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
           }
         }
         if (writer) {
+          if (ns <= 32) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            // a group spans several warps: combine through the (zero-initialised) output; values are >= +0 after the
+            // ReLU, so unsigned order == float order
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicMax(reinterpret_cast<unsigned int*>(orow + c0 + j), __float_as_uint(v[j]));
+          }
         }
       }
       tc::tc_fence_before();
@@ -208,7 +215,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     // t+1 are issued before H1 of tile t is written, so their latency never sits on the producers' critical path.
     auto row_index = [&](int tile) -> int {          // ball-query result of this thread's row, -1 beyond the end
       const long long R = (long long)tile * SF_TM + pt;
-      return (pt < SF_TM && tile < num_tiles && R < a.rows) ? __ldg(a.idx + R) : -1;
+      if (!(pt < SF_TM && tile < num_tiles && R < a.rows)) return -1;
+      return a.idx ? __ldg(a.idx + R) : (int)(R % ns);
     };
     auto row_info = [&](int tile, int i) -> float4 {
       float4 info = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
@@ -216,6 +224,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         const long long R = (long long)tile * SF_TM + pt;
         const long long cj = R / ns;
         const long long src = (cj / a.M) * a.N + i;
+        if (a.pair_scalar != nullptr) return make_float4(__ldg(a.pair_scalar + R), 0.f, 0.f, __int_as_float((int)src));
         const float* p = a.xyz + src * 3;
         const float* c = a.new_xyz + cj * 3;
         float dx = __fsub_rn(__ldg(p), __ldg(c)), dy = __fsub_rn(__ldg(p + 1), __ldg(c + 1)), dz = __fsub_rn(__ldg(p + 2), __ldg(c + 2));
@@ -434,7 +443,7 @@ extern "C" __attribute__((visibility("default"))) void ptt_debug_sa_timeline(lon
 bool sa_fused_supported(int d1, int d2, int d3, int ns) {
   const bool dims = (d1 == 64 && d2 == 64 && d3 == 128) || (d1 == 128 && d2 == 128 && d3 == 256) ||
                     (d1 == 256 && d2 == 256 && d3 == 256);
-  const bool group = ns >= 1 && ns <= 32 && (ns & (ns - 1)) == 0;
+  const bool group = ns >= 1 && ns <= SF_TM && (ns & (ns - 1)) == 0;   // whole groups per 128-row tile
   return dims && group;
 }
 
@@ -442,6 +451,11 @@ int sa_fused_launch(const SaFusedArgs& a_in, int d1, int d2, int d3, cudaStream_
   SaFusedArgs a = a_in;
   a.dbg = g_sa_dbg;
   if (a.rows <= 0) return PTT_OK;
+  if (a.ns > 32) {   // groups wider than a warp are combined with atomicMax: the output starts at +0
+    cudaError_t e = cudaMemset2DAsync(a.out_pm, (size_t)a.ld_out * sizeof(float), 0, (size_t)d3 * sizeof(float),
+                                      (size_t)(a.rows / a.ns), st);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (d1 == 64 && d2 == 64 && d3 == 128) return sf_launch<64, 64, 128>(a, st);
   if (d1 == 128 && d2 == 128 && d3 == 256) return sf_launch<128, 128, 256>(a, st);
   if (d1 == 256 && d2 == 256 && d3 == 256) return sf_launch<256, 256, 256>(a, st);

@@ -6,7 +6,9 @@
 struct SaFusedArgs {
   const float* xyz = nullptr;      // (B, N, 3)
   const float* new_xyz = nullptr;  // (B, M, 3)
-  const int* idx = nullptr;        // (B, M, ns) ball-query result
+  const int* idx = nullptr;        // (B, M, ns) ball-query result; nullptr = every centre's group is all N points in order (ns == N)
+  const float* pair_scalar = nullptr;  // optional (B, M, ns): the pair's relative part is (pair_scalar, 0, 0) instead of
+                                       // (xyz[i] - new_xyz[j]) (/ radius) -- the similarity column of CosineSimAug
   const float* gprime = nullptr;   // (B*N, D1) = scale1 * (feats . W1f^T) + shift1, or nullptr when the layer has no features
   const float* shift1 = nullptr;   // (D1) used when gprime == nullptr
   const float* wx = nullptr;       // (3, D1): scale1 * W1[:, xyz columns]

@@ -94,20 +94,23 @@ __global__ void __launch_bounds__(256) sa_group_rows_kernel(const float* __restr
                                                              int ldf, const float* __restrict__ new_xyz,
                                                              const int* __restrict__ idx, int N, int M, int ns, int C,
                                                              float radius, int normalize, long long rows,
-                                                             float* __restrict__ X, int ldx) {
+                                                             float* __restrict__ X, int ldx,
+                                                             const float* __restrict__ pair_scalar) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long row = warp; row < rows; row += nwarps) {
     const long long cj = row / ns;           // b * M + j
     const int b = (int)(cj / M);
-    const int i = __ldg(idx + row);
+    const int i = idx ? __ldg(idx + row) : (int)(row % ns);
     const float* src = feats ? feats + ((size_t)b * N + i) * ldf : nullptr;
     float* dst = X + (size_t)row * ldx;
     for (int c = lane; c < C; c += 32) dst[c] = __ldg(src + c);
     if (lane < ldx - C) {
       float v = 0.f;
-      if (lane < 3) {
+      if (pair_scalar != nullptr) {
+        if (lane == 0) v = __ldg(pair_scalar + row);
+      } else if (lane < 3) {
         v = __fsub_rn(__ldg(xyz + ((size_t)b * N + i) * 3 + lane), __ldg(new_xyz + (size_t)cj * 3 + lane));
         if (normalize) v = __fdiv_rn(v, radius);
       }
@@ -204,14 +207,18 @@ extern "C" size_t ptt_sa_mlp_workspace_bytes(int B, int N, int M, int ns, int C,
   return W.total * sizeof(float);
 }
 
-extern "C" int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, const float* new_xyz, const int* idx,
-                              int B, int N, int M, int ns, int C, float radius, int normalize_xyz, int n_layers,
-                              const int* h_dims, const float* params, float* out_pm, int ld_out, float* out_cm,
-                              void* workspace, size_t workspace_bytes, ptt_stream_t stream) {
+// pair_scalar != nullptr: the relative part of pair (j, s) is (pair_scalar[b, j, s], 0, 0) and xyz / new_xyz are unused;
+// idx == nullptr (then ns == N): every centre's group is all N points in order.
+static int sa_mlp_fwd_impl(const float* xyz, const float* feats, int ldf, const float* new_xyz, const int* idx,
+                           const float* pair_scalar, int B, int N, int M, int ns, int C, float radius, int normalize_xyz,
+                           int n_layers, const int* h_dims, const float* params, float* out_pm, int ld_out, float* out_cm,
+                           void* workspace, size_t workspace_bytes, ptt_stream_t stream) {
   SaLayout L;
   PTT_CHECK_ARG(B >= 0 && N >= 1 && M >= 0 && ns >= 1 && sa_layout(C, n_layers, h_dims, &L));
   if (B == 0 || M == 0) return PTT_OK;
-  PTT_CHECK_ARG(xyz && new_xyz && idx && params && (out_pm || out_cm));
+  PTT_CHECK_ARG(params && (out_pm || out_cm));
+  PTT_CHECK_ARG(pair_scalar != nullptr || (xyz && new_xyz));
+  PTT_CHECK_ARG(idx != nullptr || ns == N);
   PTT_CHECK_ARG(C == 0 || (feats != nullptr && ldf >= C));
   const int Cout = L.dims[n_layers];
   PTT_CHECK_ARG(out_pm == nullptr || ld_out >= Cout);
@@ -239,7 +246,7 @@ extern "C" int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, con
     float* pm = out_pm ? out_pm : ws + W.pm_off;
     const int ld_pm = out_pm ? ld_out : W.ldh;
     SaFusedArgs f;
-    f.xyz = xyz; f.new_xyz = new_xyz; f.idx = idx;
+    f.xyz = xyz; f.new_xyz = new_xyz; f.idx = idx; f.pair_scalar = pair_scalar;
     f.gprime = gprime; f.shift1 = params + L.shift[0]; f.wx = params + L.wxs;
     f.w2img = params + L.w2s; f.w3img = params + L.w3s;
     f.shift2 = params + L.shift[1]; f.shift3 = params + L.shift[2];
@@ -258,7 +265,7 @@ extern "C" int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, con
   {
     const long long blocks = llmin_((rows + 7) / 8, 148LL * 16);
     sa_group_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(xyz, feats, ldf, new_xyz, idx, N, M, ns, C, radius,
-                                                           normalize_xyz, rows, X, W.ldx); PTT_LAUNCHED();
+                                                           normalize_xyz, rows, X, W.ldx, pair_scalar); PTT_LAUNCHED();
   }
   const float* in = X;
   int ld_in = W.ldx;
@@ -285,4 +292,124 @@ extern "C" int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, con
   if (rc != PTT_OK) return rc;
   if (out_cm) rc = ptt_pm_to_cm(pm, ld_pm, B, Cout, M, out_cm, stream);
   return rc;
+}
+
+extern "C" int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, const float* new_xyz, const int* idx,
+                              int B, int N, int M, int ns, int C, float radius, int normalize_xyz, int n_layers,
+                              const int* h_dims, const float* params, float* out_pm, int ld_out, float* out_cm,
+                              void* workspace, size_t workspace_bytes, ptt_stream_t stream) {
+  PTT_CHECK_ARG(B == 0 || M == 0 || (xyz && new_xyz && idx));
+  return sa_mlp_fwd_impl(xyz, feats, ldf, new_xyz, idx, nullptr, B, N, M, ns, C, radius, normalize_xyz, n_layers, h_dims,
+                         params, out_pm, ld_out, out_cm, workspace, workspace_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CosineSimAug fusion (similarity_modules/p2b_xcoor.py:25-43): for every (search point s, template point t) the row
+//   [cos(template_feats_t, search_feats_s) | template_xyz_t | template_feats_t]      (1 + 3 + f channels)
+// goes through the SharedMLP and the result is max-pooled over the n1 templates.  Only ONE of the 1 + 3 + f input
+// channels depends on s, so this is a set-abstraction layer whose "points" are the templates (features [xyz_t | feats_t],
+// C = 3 + f), whose every group is all n1 templates, and whose relative part is (sim, 0, 0): the same fused kernel.  The
+// packed parameters are those of ptt_sa_pack_params for C = 3 + f with the layer-0 weight columns ordered
+// [w_sim, 0, 0 | W0[:, 1:]] (the binding builds it).
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// one warp per (b, s): sim[b, s, t] = (S_s / max(|S_s|, eps)) . (T_t / max(|T_t|, eps)) for all t
+__global__ void __launch_bounds__(256) cosine_sim_kernel(const float* __restrict__ S, int lds, const float* __restrict__ T,
+                                                          int ldt, int n1, int n2, int f, long long rows,
+                                                          float* __restrict__ sim) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const float eps = 1e-8f;
+  for (long long row = warp; row < rows; row += nwarps) {      // row = b * n2 + s
+    const long long b = row / n2;
+    const float* srow = S + row * lds;
+    float ss = 0.f;
+    for (int c = lane; c < f; c += 32) { const float v = __ldg(srow + c); ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv_s = 1.f / fmaxf(sqrtf(ss), eps);
+    for (int t = 0; t < n1; ++t) {
+      const float* trow = T + (b * n1 + t) * ldt;
+      float dot = 0.f, tt = 0.f;
+      for (int c = lane; c < f; c += 32) {
+        const float v = __ldg(trow + c);
+        dot = fmaf(v, __ldg(srow + c), dot);
+        tt = fmaf(v, v, tt);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        tt += __shfl_xor_sync(0xffffffffu, tt, o);
+      }
+      if (lane == 0) sim[row * n1 + t] = (dot * inv_s) * (1.f / fmaxf(sqrtf(tt), eps));
+    }
+  }
+}
+
+// X[b * n1 + t] = [template_xyz_t (3) | template_feats_t (f) | 0 pad]
+__global__ void __launch_bounds__(256) cosine_rows_kernel(const float* __restrict__ txyz, const float* __restrict__ T, int ldt,
+                                                           int f, long long rows, float* __restrict__ X, int ldx) {
+  const long long total = rows * ldx;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / ldx;
+    const int c = (int)(e - r * ldx);
+    float v = 0.f;
+    if (c < 3) v = __ldg(txyz + r * 3 + c);
+    else if (c < 3 + f) v = __ldg(T + r * ldt + (c - 3));
+    X[e] = v;
+  }
+}
+
+struct CosWorkspace {
+  int ldx;
+  size_t sim, x, sa, total;   // float offsets
+};
+bool cos_workspace(int B, int n1, int n2, int f, int n_layers, const int* h_dims, CosWorkspace* W) {
+  W->ldx = round_up(3 + f, 4);
+  size_t off = 0;
+  W->sim = off; off += align_up((size_t)B * n2 * n1, 64);
+  W->x = off;   off += align_up((size_t)B * n1 * W->ldx, 64);
+  W->sa = off;
+  const size_t sa_bytes = ptt_sa_mlp_workspace_bytes(B, n1, n2, n1, 3 + f, n_layers, h_dims);
+  if (sa_bytes == 0) return false;
+  off += sa_bytes / sizeof(float) + 64;
+  W->total = off;
+  return true;
+}
+
+}  // namespace
+
+extern "C" size_t ptt_cosine_fusion_workspace_bytes(int B, int n1, int n2, int f, int n_layers, const int* h_dims) {
+  CosWorkspace W;
+  if (B <= 0 || n1 <= 0 || n2 <= 0 || f <= 0 || !cos_workspace(B, n1, n2, f, n_layers, h_dims, &W)) return 0;
+  return W.total * sizeof(float);
+}
+
+extern "C" int ptt_cosine_fusion_fwd(const float* search_feats, int lds, const float* template_feats, int ldt,
+                                     const float* template_xyz, int B, int n1, int n2, int f, int n_layers,
+                                     const int* h_dims, const float* params, float* out_pm, int ld_out, void* workspace,
+                                     size_t workspace_bytes, ptt_stream_t stream) {
+  PTT_CHECK_ARG(B >= 0 && n1 >= 1 && n2 >= 0 && f >= 1 && lds >= f && ldt >= f && h_dims != nullptr && h_dims[0] == f + 6);
+  if (B == 0 || n2 == 0) return PTT_OK;
+  PTT_CHECK_ARG(search_feats && template_feats && template_xyz && params && out_pm);
+  CosWorkspace W;
+  PTT_CHECK_ARG(cos_workspace(B, n1, n2, f, n_layers, h_dims, &W));
+  if (workspace == nullptr || workspace_bytes < W.total * sizeof(float)) return PTT_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 15u) != 0) return PTT_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  float* ws = static_cast<float*>(workspace);
+  float* sim = ws + W.sim;
+  float* X = ws + W.x;
+  {
+    const long long rows = (long long)B * n2;
+    cosine_sim_kernel<<<(unsigned)llmin_((rows + 7) / 8, 148LL * 8), 256, 0, st>>>(search_feats, lds, template_feats, ldt, n1, n2,
+                                                                                   f, rows, sim); PTT_LAUNCHED();
+    const long long trows = (long long)B * n1;
+    cosine_rows_kernel<<<(unsigned)llmin_((trows * W.ldx + 255) / 256, 148LL * 8), 256, 0, st>>>(template_xyz, template_feats,
+                                                                                                 ldt, f, trows, X, W.ldx); PTT_LAUNCHED();
+  }
+  return sa_mlp_fwd_impl(nullptr, X, W.ldx, nullptr, nullptr, sim, B, n1, n2, n1, 3 + f, 1.f, 0, n_layers, h_dims, params,
+                         out_pm, ld_out, nullptr, ws + W.sa, workspace_bytes - W.sa * sizeof(float), stream);
 }

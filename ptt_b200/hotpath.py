@@ -63,6 +63,14 @@ class HotPath:
         self.centroid_tr = ops.PackedTransformer(_sub(sd, "centroid_voting_head.transformer_block."), self.cfg["knn"])
         self.box_sa = pack_sa_module(_sub(sd, "box_voting_head.vote_aggregation."), eps)
         self.box_tr = ops.PackedTransformer(_sub(sd, "box_voting_head.transformer_block."), self.cfg["knn"])
+        # SURVEY.md 8(f) N1 / N2, present when the state_dict carries them: the similarity module and the heads' Conv1d
+        # stacks, so that forward_full() is the whole tracker forward (trackers/ptt.py:45-46)
+        self.full = "similarity_module.mlp.layer0.conv.weight" in sd
+        if self.full:
+            self.cosine = ops.PackedCosineFusion(_sub(sd, "similarity_module."), eps)
+            self.cla = ops.PackedConvStack(_sub(sd, "centroid_voting_head.cla_layer."), eps)
+            self.vote = ops.PackedConvStack(_sub(sd, "centroid_voting_head.vote_layer."), eps)
+            self.refine = ops.PackedConvStack(_sub(sd, "box_voting_head.refine_layer."), eps)
         self.streams = None
         self.use_graph = True         # forward_host replays a captured CUDA graph
         self.overlap = True           # template branch on a second stream (False: one stream, for per-stage timing)
@@ -190,6 +198,73 @@ class HotPath:
                 "centroid_feats": cen, "box_centers": b_xyz, "box_sa_feats": b_feat, "box_feats": box}
 
     __call__ = forward
+
+    # ------------------------------------------------------------------------------------------------
+    # The whole tracker forward, eval mode (trackers/ptt.py:45-46 over ptt.yaml's module list): backbone ->
+    # CosineSimAug (p2b_xcoor.py:25-46) -> CentroidVotingHead (centroids_voting_head.py:66-100) -> BoxVotingHead
+    # (box_voting_head.py:70-95).  Returns the reference's batch_dict entries with the reference's layouts.
+    # ------------------------------------------------------------------------------------------------
+    def forward_full(self, search, template):
+        if not self.full:
+            raise RuntimeError("forward_full needs the similarity_module / head parameters in the state_dict")
+        c = self.cfg
+        if self.streams is None:
+            self.streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        cur = torch.cuda.current_stream()
+        s1, s2 = self.streams if self.overlap else (self.streams[0], self.streams[0])
+        s1.wait_stream(cur)
+        s2.wait_stream(cur)
+        with torch.cuda.stream(s2):
+            t_xyz, t_feat_pm, t_inds = self.backbone_branch(template, c["npoints_template"], "template")
+            t_feat = ops.pm_to_cm(t_feat_pm)
+        with torch.cuda.stream(s1):
+            s_xyz, s_feat_pm, s_inds = self.backbone_branch(search, c["npoints_search"])
+            s_feat = ops.pm_to_cm(s_feat_pm)
+            s1.wait_stream(s2)
+            B, n, _ = s_xyz.shape
+            # ---- similarity module
+            ws = self._workspace("cosine", self.cosine.workspace_bytes(B, t_xyz.shape[1], n))
+            with self._Stage(self, "cosine.fusion"):
+                cos_pm = self.cosine(s_feat_pm, t_feat_pm, t_xyz, workspace=ws)
+            # ---- centroid head
+            ws = self._workspace("centroid.transformer", self.centroid_tr.workspace_bytes(B, n))
+            with self._Stage(self, "centroid.transformer"):
+                cen = ops.transformer_block_fwd(self.centroid_tr, s_xyz, cos_pm, workspace=ws)
+            with self._Stage(self, "centroid.heads"):
+                d = cen.shape[2]
+                cls = self.cla(cen.reshape(B * n, d)).reshape(B, n)                           # :87
+                ldv = (3 + d + 3) // 4 * 4
+                vin = torch.zeros(B, n, ldv, dtype=cen.dtype, device=cen.device)               # voting_input = [xyz | feats]  :92
+                vin[:, :, :3] = s_xyz
+                vin[:, :, 3:3 + d] = cen
+                res = self.vote(vin.reshape(B * n, ldv), residual=vin.reshape(B * n, ldv)).reshape(B, n, 3 + d)   # :93-95
+                votes = res[:, :, :3].contiguous()
+                vf = torch.zeros(B, n, (d + 1 + 3) // 4 * 4, dtype=cen.dtype, device=cen.device)   # [score | results[3:]]  :100
+                vf[:, :, 0] = torch.sigmoid(cls)
+                vf[:, :, 1:1 + d] = res[:, :, 3:]
+            # ---- box head
+            b_xyz, b_feat_pm, _, _ = self._sa_layer(self.box_sa, votes, vf, c["box_npoint"], c["box_radius"],
+                                                    c["box_nsample"], "fps", tag="box.sa")
+            ws = self._workspace("box.transformer", self.box_tr.workspace_bytes(B, b_xyz.shape[1]))
+            with self._Stage(self, "box.transformer"):
+                box = ops.transformer_block_fwd(self.box_tr, b_xyz, b_feat_pm, workspace=ws)
+            with self._Stage(self, "box.heads"):
+                m = b_xyz.shape[1]
+                est = self.refine(box.reshape(B * m, box.shape[2])).reshape(B, m, -1)           # :88
+                est[:, :, :3] += b_xyz                                                           # :90-91
+            cos_cm = ops.pm_to_cm(cos_pm)
+            vf_cm = ops.pm_to_cm(vf[:, :, :d + 1].contiguous())
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+        out = {"search_seeds": s_xyz, "search_feats": s_feat, "search_inds": s_inds,
+               "template_seeds": t_xyz, "template_feats": t_feat, "template_inds": t_inds,
+               "cosine_feats": cos_cm, "centroid_feats": cen, "pred_centroids_cls": cls, "pred_centroids_votes": votes,
+               "votes_feats": vf_cm, "pred_box_center": b_xyz, "box_sa_feats": b_feat_pm, "box_feats": box,
+               "pred_box_data": est}
+        if not torch.cuda.is_current_stream_capturing():
+            for t in list(out.values()) + [t_feat_pm, s_feat_pm, cos_pm, vin, res, vf]:
+                t.record_stream(cur)
+        return out
 
     # ------------------------------------------------------------------------------------------------
     # CUDA-graph replay: the ~110 launches of one step are captured once per input shape and replayed

@@ -244,16 +244,56 @@ class PackedLinear:
                   "ptt_linear_pack")
 
     def __call__(self, x, relu=False, residual=None):
+        """x (R, ldx >= K): the first K columns of every row are the input (rows padded to a multiple of 4 floats take
+        the tensor-core path); residual (R, ldr >= Cout) is added after the activation."""
         _req(x, _F, 2, "x")
-        R, K = x.shape
-        if K != self.k:
-            raise PttError("linear: x has %d columns, weight expects %d" % (K, self.k))
+        R, ldx = x.shape
+        if ldx < self.k:
+            raise PttError("linear: x has %d columns, weight expects %d" % (ldx, self.k))
+        ldr = 0
+        if residual is not None:
+            _req(residual, _F, 2, "residual")
+            ldr = residual.shape[1]
+            if residual.shape[0] != R or ldr < self.cout:
+                raise PttError("linear: residual must be (R, ld >= Cout)")
         with _DeviceGuard(x.device):
             y = torch.empty(R, self.cout, dtype=_F, device=x.device)
-            check(_lib.lib().ptt_linear_fwd(_ptr(x), K, R, K, _ptr(self.params), self.cout, int(relu), _ptr(residual),
-                                            self.cout if residual is not None else 0, _ptr(y), self.cout, _stream()),
+            check(_lib.lib().ptt_linear_fwd(_ptr(x), ldx, R, self.k, _ptr(self.params), self.cout, int(relu), _ptr(residual),
+                                            ldr, _ptr(y), self.cout, _stream()),
                   "ptt_linear_fwd")
         return y
+
+
+class PackedConvStack:
+    """pytorch_utils.Seq of 1x1 Conv1d layers (pytorch_utils.py:270-300; keys {i}.conv.weight (Cout,Cin,1), {i}.conv.bias,
+    {i}.normlayer.bn.*) in eval mode: BatchNorm folded into the weights, ReLU after every layer but the last -- the
+    heads' cla / vote / refine stacks and the similarity module's conv all end with activation=None
+    (centroids_voting_head.py:14-25, box_voting_head.py:24-29, p2b_xcoor.py:20-24).  Rows are points."""
+
+    def __init__(self, sd, eps=1e-5):
+        self.layers = []
+        i = 0
+        while "%d.conv.weight" % i in sd:
+            p = "%d." % i
+            w = sd[p + "conv.weight"]
+            w = w.reshape(w.shape[0], w.shape[1])
+            b = sd.get(p + "conv.bias")
+            if p + "normlayer.bn.weight" in sd:
+                scale, shift = fold_batchnorm(sd[p + "normlayer.bn.weight"], sd[p + "normlayer.bn.bias"],
+                                              sd[p + "normlayer.bn.running_mean"], sd[p + "normlayer.bn.running_var"], eps)
+                w = w * scale[:, None]
+                b = shift if b is None else shift + scale * b
+            self.layers.append(PackedLinear(w.contiguous(), b.contiguous() if b is not None else None))
+            i += 1
+        if not self.layers:
+            raise PttError("PackedConvStack: no layers in the state_dict")
+        self.cout = self.layers[-1].cout
+
+    def __call__(self, x, residual=None):
+        n = len(self.layers)
+        for i, lin in enumerate(self.layers):
+            x = lin(x, relu=i < n - 1, residual=residual if i == n - 1 else None)
+        return x
 
 
 # ------------------------------------------------------------------------------------------------
@@ -323,6 +363,60 @@ def sa_mlp_fwd(packed, xyz, feats_pm, new_xyz, idx, radius, normalize_xyz, want_
                                _ptr(packed.params), _ptr(out_pm), packed.cout, _ptr(out_cm), _ptr(ws),
                                ws.numel() * 4, _stream()), "ptt_sa_mlp_fwd")
     return out_pm, out_cm
+
+
+class PackedCosineFusion:
+    """CosineSimAug (similarity_modules/p2b_xcoor.py:9-46), eval mode, from its state_dict (keys mlp.layer{i}.*, conv.{i}.*).
+
+    The (1 + 3 + f)-channel fusion rows only depend on the search point through ONE channel (the cosine similarity), so
+    the SharedMLP + max over the templates is a set-abstraction layer over the templates (ptt_cosine_fusion_fwd)."""
+
+    def __init__(self, sd, eps=1e-5):
+        ws, scales, shifts = [], [], []
+        i = 0
+        while "mlp.layer%d.conv.weight" % i in sd:
+            p = "mlp.layer%d." % i
+            w = sd[p + "conv.weight"]
+            w = w.reshape(w.shape[0], w.shape[1])
+            if i == 0:      # reference columns [sim | xyz_t(3) | feats_t(f)] -> SA order [rel(3) = (sim, 0, 0) | point features]
+                w = torch.cat([w[:, :1], torch.zeros_like(w[:, :2]), w[:, 1:]], dim=1)
+            ws.append(w.contiguous())
+            if p + "normlayer.bn.weight" in sd:
+                sc, sh = fold_batchnorm(sd[p + "normlayer.bn.weight"], sd[p + "normlayer.bn.bias"],
+                                        sd[p + "normlayer.bn.running_mean"], sd[p + "normlayer.bn.running_var"], eps)
+                if p + "conv.bias" in sd:
+                    sh = sh + sd[p + "conv.bias"] * sc
+            else:
+                sc, sh = None, sd.get(p + "conv.bias")
+            scales.append(sc)
+            shifts.append(sh)
+            i += 1
+        self.mlp = PackedSAMlp(ws, scales, shifts)
+        self.f = self.mlp.C - 3
+        n = len("conv.")
+        self.conv = PackedConvStack({k[n:]: v for k, v in sd.items() if k.startswith("conv.")}, eps)
+
+    def workspace_bytes(self, B, n1, n2):
+        return _lib.lib().ptt_cosine_fusion_workspace_bytes(B, n1, n2, self.f, self.mlp.n_layers, self.mlp.h_dims)
+
+    def __call__(self, search_feats_pm, template_feats_pm, template_xyz, workspace=None):
+        """search_feats_pm (B,n2,f), template_feats_pm (B,n1,f), template_xyz (B,n1,3) -> cosine_feats_pm (B,n2,Cout)."""
+        _req(search_feats_pm, _F, 3, "search_feats_pm"), _req(template_feats_pm, _F, 3, "template_feats_pm")
+        _req(template_xyz, _F, 3, "template_xyz")
+        dev = _same_device(search_feats_pm, template_feats_pm, template_xyz)
+        B, n2, lds = search_feats_pm.shape
+        _, n1, ldt = template_feats_pm.shape
+        if lds < self.f or ldt < self.f or template_feats_pm.shape[0] != B or tuple(template_xyz.shape) != (B, n1, 3):
+            raise PttError("cosine fusion: inconsistent shapes")
+        L = _lib.lib()
+        with _DeviceGuard(dev):
+            fused = torch.empty(B, n2, self.mlp.cout, dtype=_F, device=dev)
+            ws_bytes = self.workspace_bytes(B, n1, n2)
+            ws = workspace if workspace is not None else _workspace(ws_bytes, dev)
+            check(L.ptt_cosine_fusion_fwd(_ptr(search_feats_pm), lds, _ptr(template_feats_pm), ldt, _ptr(template_xyz), B, n1,
+                                          n2, self.f, self.mlp.n_layers, self.mlp.h_dims, _ptr(self.mlp.params), _ptr(fused),
+                                          self.mlp.cout, _ptr(ws), ws.numel() * 4, _stream()), "ptt_cosine_fusion_fwd")
+        return self.conv(fused.reshape(B * n2, self.mlp.cout)).reshape(B, n2, -1)
 
 
 TRANSFORMER_KEYS = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc_delta.0.weight", "fc_delta.0.bias",

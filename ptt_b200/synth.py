@@ -183,6 +183,41 @@ def hot_path_layout():
     return sd
 
 
+def seq_layout(channels, bn_last=False, prefix=""):
+    """pytorch_utils.Seq of Conv1d layers: BatchNorm (no conv bias) on every layer but the last, which has a bias."""
+    sd = {}
+    n = len(channels) - 1
+    for i in range(n):
+        p = "%s%d." % (prefix, i)
+        sd[p + "conv.weight"] = (channels[i + 1], channels[i], 1)
+        if i < n - 1 or bn_last:
+            for k in ("weight", "bias", "running_mean", "running_var"):
+                sd[p + "normlayer.bn." + k] = (channels[i + 1],)
+            sd[p + "normlayer.bn.num_batches_tracked"] = ()
+        else:
+            sd[p + "conv.bias"] = (channels[i + 1],)
+    return sd
+
+
+def full_model_layout():
+    """Every parameter of a PTT tracker under tools/cfgs/kitti_models/ptt.yaml that the eval forward reads: the hot
+    path plus the similarity module and the heads' Conv1d stacks."""
+    sd = hot_path_layout()
+    mlp = sa_layout([260, 256, 256, 256], use_xyz=False, prefix="similarity_module.")
+    sd.update({k.replace("similarity_module.mlp_module.", "similarity_module.mlp."): v for k, v in mlp.items()})
+    sd.update(seq_layout([256, 256, 256], prefix="similarity_module.conv."))
+    sd.update(seq_layout([256, 256, 256, 1], prefix="centroid_voting_head.cla_layer."))
+    sd.update(seq_layout([259, 256, 256, 259], prefix="centroid_voting_head.vote_layer."))
+    sd.update(seq_layout([256, 256, 256, 5], prefix="box_voting_head.refine_layer."))
+    return sd
+
+
+def full_model_state_dict(seed=0):
+    import torch
+
+    return {k: torch.from_numpy(v) for k, v in fill_state_dict(full_model_layout(), seed).items()}
+
+
 def hot_path_state_dict(seed=0):
     """Filled hot-path parameters as torch CPU tensors."""
     import torch

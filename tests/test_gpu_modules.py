@@ -272,3 +272,80 @@ def test_transformer_std_vs_port(shape):
     got, attn = ops.transformer_std_fwd(packed, g(xyz), g(f))
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), **FP_TOL)
     np.testing.assert_allclose(attn.cpu().numpy(), want_attn.numpy(), **FP_TOL)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the similarity module and the heads' Conv1d stacks -> the whole tracker forward
+# ------------------------------------------------------------------------------------------------------------------
+def _sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 128, 256), (2, 16, 40, 256), (2, 24, 33, 256), (1, 128, 8, 256)])
+def test_cosine_fusion_vs_port(shape):
+    """CosineSimAug: fused path (n1 a power of two) and the generic path (n1 = 24), against the port."""
+    B, n1, n2, f = shape
+    sd = {k: v for k, v in synth.full_model_state_dict(3).items() if k.startswith("similarity_module.")}
+    sd = _sub(sd, "similarity_module.")
+    s_feat = synth.features((B, n2, f), seed=900 + n1)
+    t_feat = synth.features((B, n1, f), seed=901 + n1)
+    t_xyz = synth.make_clouds(B, n1, 902, "dense", role="template")
+    cf = ops.PackedCosineFusion({k: g(v) for k, v in sd.items()})
+    got = cf(g(s_feat), g(t_feat), g(t_xyz))
+    want = torch_port.cosine_sim_aug(sd, t(s_feat).transpose(1, 2).contiguous(), t(t_feat).transpose(1, 2).contiguous(), t(t_xyz))
+    np.testing.assert_allclose(got.cpu().numpy(), want.transpose(1, 2).numpy(), **FP_TOL)
+
+
+def _check_full(out, want, sd, cfg=None):
+    """Stage-by-stage comparison of HotPath.forward_full with the port.  The box head starts with FPS over the
+    PREDICTED votes, where a 1e-6 difference may legitimately flip a pick, so its reference is the port's box head
+    run on the votes the GPU produced (identical FPS input); when the picks agree with the port's own end-to-end run
+    as well (they do on the committed cases) the final boxes are compared directly too."""
+    for k in ("search_inds", "template_inds"):
+        assert np.array_equal(out[k].cpu().numpy(), want[k].numpy()), k
+    for k in ("search_feats", "template_feats", "cosine_feats", "pred_centroids_cls", "pred_centroids_votes", "votes_feats"):
+        np.testing.assert_allclose(out[k].cpu().numpy(), want[k].numpy(), err_msg=k, **FP_TOL)
+    np.testing.assert_allclose(out["centroid_feats"].cpu().numpy(), want["centroid_feats"].numpy(), **FP_TOL)
+    c = dict(knn=16, box_npoint=64, box_radius=0.3, box_nsample=16)
+    c.update(cfg or {})
+    b_xyz, box_data, b_feat, box = torch_port.box_voting_head(_sub(sd, "box_voting_head."), out["pred_centroids_votes"].cpu(),
+                                                              out["votes_feats"].cpu(), c)
+    assert np.array_equal(out["pred_box_center"].cpu().numpy(), b_xyz.numpy())
+    np.testing.assert_allclose(out["box_sa_feats"].cpu().numpy(), b_feat.transpose(1, 2).numpy(), **FP_TOL)
+    np.testing.assert_allclose(out["box_feats"].cpu().numpy(), box.numpy(), **FP_TOL)
+    np.testing.assert_allclose(out["pred_box_data"].cpu().numpy(), box_data.numpy(), **FP_TOL)
+    same_picks = np.allclose(out["pred_box_center"].cpu().numpy(), want["pred_box_center"].numpy(), rtol=1e-5, atol=1e-4)
+    if same_picks:
+        np.testing.assert_allclose(out["pred_box_data"].cpu().numpy(), want["pred_box_data"].numpy(), **FP_TOL)
+    return same_picks
+
+
+def test_full_model_vs_reference_fixture(golden):
+    """The whole tracker forward on the GPU against what the REFERENCE's own PTT model produced (full/*)."""
+    gd = golden("hot_path.npz")
+    sd = synth.full_model_state_dict(0)
+    hp = hotpath.HotPath(sd, device=DEV)
+    out = hp.forward_full(g(gd["full/search"]), g(gd["full/template"]))
+    torch.cuda.synchronize()
+    for k in ("search_feats", "template_feats", "cosine_feats", "pred_centroids_cls", "pred_centroids_votes"):
+        np.testing.assert_allclose(out[k].cpu().numpy(), gd["full/" + k], err_msg=k, **FP_TOL)
+    want = torch_port.full_model_frame(sd, t(gd["full/search"]), t(gd["full/template"]))
+    same = _check_full(out, want, sd)
+    assert same, "box-centre FPS picks differ from the reference run"
+    np.testing.assert_allclose(out["pred_box_center"].cpu().numpy(), gd["full/pred_box_center"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(out["pred_box_data"].cpu().numpy(), gd["full/pred_box_data"], **FP_TOL)
+
+
+def test_full_model_sparse_and_small_vs_port():
+    sd = synth.full_model_state_dict(1)
+    hp = hotpath.HotPath(sd, device=DEV)
+    search, template = synth.make_clouds(3, 512, 910, "sparse"), synth.make_clouds(3, 512, 911, "sparse", role="template")
+    out = hp.forward_full(g(search), g(template))
+    torch.cuda.synchronize()
+    _check_full(out, torch_port.full_model_frame(sd, t(search), t(template)), sd)
+    cfg = dict(npoints_search=(128, 64, 32), npoints_template=(64, 32, 16), box_npoint=16)
+    hp = hotpath.HotPath(sd, cfg=cfg, device=DEV)
+    search, template = synth.make_clouds(2, 256, 912, "dense"), synth.make_clouds(2, 128, 913, "dense", role="template")
+    out = hp.forward_full(g(search), g(template))
+    torch.cuda.synchronize()
+    _check_full(out, torch_port.full_model_frame(sd, t(search), t(template), cfg), sd, cfg)

@@ -158,3 +158,19 @@ def test_port_transformer_vs_reference_fixture(golden, name):
         res, attn = torch_port.transformer_block(sd, xyz, t(f), k, variant=cls)
     np.testing.assert_allclose(res.numpy(), g[name + "/res"], **FP_TOL)
     np.testing.assert_allclose(attn[:, :4].numpy(), g[name + "/attn_head"], **FP_TOL)
+
+
+FULL_KEYS = ("search_feats", "template_feats", "cosine_feats", "pred_centroids_cls", "pred_centroids_votes",
+             "pred_box_center", "pred_box_data")
+
+
+def test_port_full_model_vs_reference_fixture(golden):
+    """The whole tracker forward of the port (backbone -> CosineSimAug -> both heads) against
+    the outputs of the REFERENCE's own PTT model (hot_path.npz full/*, made by make_golden.py)."""
+    g = golden("hot_path.npz")
+    sd = synth.full_model_state_dict(0)
+    out = torch_port.full_model_frame(sd, t(g["full/search"]), t(g["full/template"]))
+    # FPS over the predicted votes: same picks (the values themselves carry the votes' 1e-6 summation-order noise)
+    np.testing.assert_allclose(out["pred_box_center"].numpy(), g["full/pred_box_center"], rtol=1e-5, atol=1e-4)
+    for k in FULL_KEYS:
+        np.testing.assert_allclose(out[k].numpy(), g["full/" + k], err_msg=k, **FP_TOL)
