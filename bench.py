@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--kind", default="dense", choices=["dense", "sparse"])
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-whole-model", action="store_true", help="skip the whole-tracker-forward figure")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
     return ap.parse_args()
 
@@ -310,6 +311,34 @@ def run_b200(a):
     barrier()
     e2e_sync_s = time.perf_counter() - t0
 
+    # ---- whole tracker forward (hot path + CosineSimAug + the heads' Conv1d stacks; SURVEY.md 8(d) "also report"):
+    # sequential CUDA-graph replays, events per step, L2 flushed between steps
+    whole = None
+    if not a.no_whole_model:
+        hpf = hotpath.HotPath(synth.full_model_state_dict(0), cfg=scaled_cfg(a), device=dev)
+        for i in range(max(3, a.warmup)):
+            hpf.forward_graph(search_d[i % n_sets], templ_d[i % n_sets], full=True)
+        barrier()
+        evw = []
+        for i in range(a.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            hpf.forward_graph(search_d[i % n_sets], templ_d[i % n_sets], full=True)
+            e1.record()
+            evw.append((e0, e1))
+        barrier()
+        whole_ms = sum(x.elapsed_time(y) for x, y in evw)
+        hpf.profile(True)
+        hpf.overlap = False
+        for i in range(min(a.steps, 5)):
+            hpf.forward_full(search_d[i % n_sets], templ_d[i % n_sets])
+        barrier()
+        wst = hpf.stage_ms(median=True)
+        whole = (shard.max_over_ranks([whole_ms], device=dev)[0], {k: round(v, 4) for k, v in sorted(wst.items())
+                                                                    if k.startswith(("cosine", "centroid.heads", "box.heads"))})
+        del hpf
+
     dev_ms, e2e_ms, wall_ms, pipe_ms = shard.max_over_ranks([dev_ms, e2e_s * 1e3, t_wall * 1e3, pipe_ms], device=dev)   # slowest rank
 
     if rank == 0:
@@ -351,6 +380,12 @@ def run_b200(a):
             "launch_mode": "eager" if a.no_graph else "CUDA graph replay (stage_ms / roofline from an eager single-stream pass of the same steps)",
             "wall_ms_per_step_incl_flush": wall_ms / a.steps,
         }
+        if whole is not None:
+            line["whole_model"] = {"value": shard.whole_job_throughput(B * a.steps, n_gpus, whole[0] * 1e-3), "unit": UNIT,
+                                   "ms_per_step": whole[0] / a.steps, "extra_stage_ms": whole[1],
+                                   "what": "HotPath.forward_full: the whole tracker forward in eval mode (hot path + CosineSimAug "
+                                           "+ cla / vote / refine stacks -> pred_box_data), one CUDA-graph replay at a time, L2 "
+                                           "flushed between steps"}
         if not a.no_cpu_baseline and world == 1:
             cpu_threads = os.cpu_count() or 1
             fps, sec = cpu_hot_path(a, a.cpu_frames, cpu_threads, steps=3, warmup=1)

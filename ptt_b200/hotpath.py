@@ -270,11 +270,12 @@ class HotPath:
     # CUDA-graph replay: the ~110 launches of one step are captured once per input shape and replayed
     # from static buffers, so the step is not bound by launch latency / Python.
     # ------------------------------------------------------------------------------------------------
-    def forward_graph(self, search, template):
-        """Same result as forward(); the first call with a given shape warms up and captures, later calls copy
+    def forward_graph(self, search, template, full=False):
+        """Same result as forward(); (full=True: forward_full()); the first call with a given shape warms up and captures, later calls copy
         the inputs into the captured buffers and replay.  The returned tensors are the graph's static outputs
         (overwritten by the next call)."""
-        key = (tuple(search.shape), tuple(template.shape))
+        key = (tuple(search.shape), tuple(template.shape), bool(full))
+        fwd = self.forward_full if full else self.forward
         g = getattr(self, "_graphs", None)
         if g is None:
             g = self._graphs = {}
@@ -287,12 +288,12 @@ class HotPath:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                      # warm-up: one-time kernel attribute calls, allocator pools
                 for _ in range(2):
-                    self.forward(static_s, static_t)
+                    fwd(static_s, static_t)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out = self.forward(static_s, static_t)
+                out = fwd(static_s, static_t)
             if was_profiling:
                 self.stage_events = {}
             g[key] = (graph, static_s, static_t, out)
