@@ -186,6 +186,31 @@ PTT_API int ptt_transformer_block_fwd(const float* xyz, const float* features, i
                               float* out, float* attn_or_null, void* workspace, size_t workspace_bytes,
                               ptt_stream_t stream);
 
+/* a10 / N4: the same kNN vector-attention core for the other registered blocks (transformer_block/__init__.py:7-17):
+ *   variant_flags   bit 0 = Offset (variants.py:297-334); bit 1 = raw: out (B,n,d_model) is the aggregated `res`,
+ *                   no fc2 / residual (TransformerBlockMLP's two-layer fc2 :225-229, MulHeadTransformerLayer's proj +
+ *                   LayerNorms multitransformer.py:61-63 and TransformerBlockBackbone :294 finish it themselves)
+ *   q_features      CrossAttentionBlock (variants.py:190-208): the queries are w_qs(fc1(q_features)); NULL = features
+ *   divisor_or_0    softmax temperature (MulHeadTransformerLayer: sqrt(head_dim)); 0 = sqrt(d_model)
+ *   pair_scalar/vec TransformerBlockCosine (variants.py:66-88): fc_gamma.0's pre-activation += pair_scalar[b,i,j] *
+ *                   pair_vec[c] (the similarity column of fc_sim pushed through fc_gamma.0); both or neither;
+ *                   d_model in {64,128,256,512} only (PTT_ERR_UNSUPPORTED otherwise)                               */
+PTT_API int ptt_transformer_block_fwd_ex(const float* xyz, const float* features, const float* q_features_or_null, int B,
+                                 int n, int k, int d_points, int d_model, int variant_flags, float divisor_or_0,
+                                 const float* params, const int* knn_idx_or_null, const float* pair_scalar_or_null,
+                                 const float* pair_vec_or_null, float* out, float* attn_or_null, void* workspace,
+                                 size_t workspace_bytes, ptt_stream_t stream);
+/* sim (B,n,k) = cos(q[b,i,:], kmat[b,knn[b,i,j],:]) with F.cosine_similarity's eps = 1e-8 (variants.py:78-79) */
+PTT_API int ptt_pair_cosine(const float* q, int ldq, const float* kmat, int ldk, const int* knn, int B, int n, int k,
+                    int d, float* sim, ptt_stream_t stream);
+/* y = LayerNorm_C(x) * gamma + beta (+ residual), rows of C channels (multitransformer.py:31-32,62-63) */
+PTT_API int ptt_layer_norm_fwd(const float* x, int ldx, int R, int C, const float* gamma, const float* beta, float eps,
+                       const float* residual_or_null, int ldr, float* y, int ldy, ptt_stream_t stream);
+/* TransformerBlockALL (variants.py:111-124): out[b,i,c] = softmax_i(logits[b,:,c] / divisor) * other[b,i,c];
+ * attn_or_null (B,n,C) receives the softmax */
+PTT_API int ptt_token_softmax_gate(const float* logits, int ldl, const float* other, int ldo, int B, int n, int C,
+                           float divisor, float* out, int ldy, float* attn_or_null, ptt_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a10 TransformerBlockSTD.forward (dense n x n dot-product attention)   transformer_block/variants.py:12-40
  *   features (B,n,d_points) -> out (B,n,d_points); attn (B,n,n) or NULL.  Parameter tensors are the reference

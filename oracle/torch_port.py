@@ -264,3 +264,80 @@ def full_model_frame(sd, search, template, cfg=None):
             "cosine_feats": cos, "centroid_feats": cen, "pred_centroids_cls": cls_out, "pred_centroids_votes": votes,
             "votes_feats": votes_feats, "pred_box_center": b_xyz, "box_sa_feats": b_feat, "box_feats": box,
             "pred_box_data": box_data}
+
+
+# ----------------------------------------------------------------------------------------------
+# a10 / N4: the other blocks of transformer_block/__init__.py:7-17
+# ----------------------------------------------------------------------------------------------
+def transformer_block_cosine(sd, xyz, features, k):
+    """TransformerBlockCosine.forward (variants.py:66-88)."""
+    knn_idx = knn_indices(xyz, k)
+    x = _linear(sd, "fc1", features)
+    q, kk, v = _linear(sd, "w_qs", x), _gather_rows(_linear(sd, "w_ks", x), knn_idx), _gather_rows(_linear(sd, "w_vs", x), knn_idx)
+    pos = _mlp2(sd, "fc_delta", xyz[:, :, None] - _gather_rows(xyz, knn_idx))
+    sim = F.cosine_similarity(q.unsqueeze(-2).repeat(1, 1, k, 1), kk, dim=-1)                      # :78-79
+    rel = _linear(sd, "fc_sim", torch.cat((sim.unsqueeze(-1), q[:, :, None] - kk), dim=-1))         # :80-82
+    attn = F.softmax(_mlp2(sd, "fc_gamma", rel + pos) / math.sqrt(kk.size(-1)), dim=-2)             # :83-84
+    res = torch.einsum("bmnf,bmnf->bmf", attn, v + pos)
+    return _linear(sd, "fc2", res) + features, attn
+
+
+def transformer_block_all(sd, xyz, features):
+    """TransformerBlockALL.forward (variants.py:111-124): softmax over the n tokens (dim=-2 of (b, n, d_model))."""
+    x = _linear(sd, "fc1", features)
+    q, kk, v = _linear(sd, "w_qs", x), _linear(sd, "w_ks", x), _linear(sd, "w_vs", x)
+    pos = _mlp2(sd, "fc_delta", xyz)
+    attn = F.softmax(_mlp2(sd, "fc_gamma", q - kk + pos) / math.sqrt(kk.size(-1)), dim=-2)
+    return _linear(sd, "fc2", attn * (v + pos)) + features, attn
+
+
+def cross_attention_block(sd, xyz, search_feat, template_feat, k):
+    """CrossAttentionBlock.forward (variants.py:190-208)."""
+    knn_idx = knn_indices(xyz, k)
+    s, tm = _linear(sd, "fc1", search_feat), _linear(sd, "fc1", template_feat)
+    q = _linear(sd, "w_qs", tm)
+    kk, v = _gather_rows(_linear(sd, "w_ks", s), knn_idx), _gather_rows(_linear(sd, "w_vs", s), knn_idx)
+    pos = _mlp2(sd, "fc_delta", xyz[:, :, None] - _gather_rows(xyz, knn_idx))
+    attn = F.softmax(_mlp2(sd, "fc_gamma", q[:, :, None] - kk + pos) / math.sqrt(kk.size(-1)), dim=-2)
+    res = torch.einsum("bmnf,bmnf->bmf", attn, v + pos)
+    return _linear(sd, "fc3", res) + search_feat, attn
+
+
+def transformer_block_backbone(sd, new_xyz, grouped_xyz, grouped_idx, features):
+    """TransformerBlockBackbone.forward (variants.py:281-294), without its debug prints."""
+    idx = grouped_idx.long()
+    x = _linear(sd, "fc1", features)
+    q, kk, v = _linear(sd, "w_qs", x), _gather_rows(_linear(sd, "w_ks", x), idx), _gather_rows(_linear(sd, "w_vs", x), idx)
+    pos = _mlp2(sd, "fc_delta", new_xyz[:, :, None] - grouped_xyz.permute(0, 2, 3, 1).contiguous())
+    attn = F.softmax(_mlp2(sd, "fc_gamma", q[:, :, None] - kk + pos) / math.sqrt(kk.size(-1)), dim=-2)
+    return torch.einsum("bmnf,bmnf->bmf", attn, v + pos).contiguous()
+
+
+def mul_head_transformer_layer(sd, xyz, features, k, heads, eps=1e-5):
+    """MulHeadTransformerLayer.forward (multitransformer.py:38-63), dropout p = 0."""
+    knn_idx = knn_indices(xyz, k)
+    x = _linear(sd, "fc1", features)
+    B, N, C = x.shape
+    query = _linear(sd, "w_qs", x).view(B, N, heads, -1).permute(0, 2, 1, 3).flatten(0, 1)
+
+    def split(t):
+        return t.view(B, N, t.shape[2], heads, -1).permute(0, 3, 1, 2, 4).flatten(0, 1)                # :51-53
+
+    key, value = split(_gather_rows(_linear(sd, "w_ks", x), knn_idx)), split(_gather_rows(_linear(sd, "w_vs", x), knn_idx))
+    pos = split(_mlp2(sd, "fc_delta", xyz[:, :, None] - _gather_rows(xyz, knn_idx)))
+    attn = F.softmax(_mlp2(sd, "fc_gamma", query[:, :, None] - key + pos) / math.sqrt(key.size(-1)), dim=-2)
+    res = torch.einsum("bmnf,bmnf->bmf", attn, value + pos)
+    if heads > 1:
+        res = res.permute(0, 2, 1).reshape(B, C, N).permute(0, 2, 1)                                    # :59-60
+    res = F.layer_norm(F.linear(res, sd["proj.weight"]), (C,), sd["norm1.weight"], sd["norm1.bias"], eps)
+    dp = features.shape[2]
+    return F.layer_norm(_linear(sd, "fc2", res), (dp,), sd["norm2.weight"], sd["norm2.bias"], eps) + features, attn
+
+
+def mul_transformer_block(sd, xyz, features, k, heads):
+    """MulTransformerBlock.forward (multitransformer.py:72-76); keys layers.{i}.*."""
+    out, attn, i = features, None, 0
+    while "layers.%d.fc1.weight" % i in sd:
+        out, attn = mul_head_transformer_layer(_sub(sd, "layers.%d." % i), xyz, out, k, heads)
+        i += 1
+    return out, attn

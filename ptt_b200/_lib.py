@@ -50,6 +50,11 @@ SIGNATURES = {
     "ptt_transformer_block_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "ptt_transformer_block_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P,
                                           c_size_t, _P]),
+    "ptt_transformer_block_fwd_ex": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P,
+                                             _P, _P, c_size_t, _P]),
+    "ptt_pair_cosine": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "ptt_layer_norm_fwd": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_float, _P, c_int, _P, c_int, _P]),
+    "ptt_token_softmax_gate": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_float, _P, c_int, _P, _P]),
     "ptt_transformer_std_params_floats": (c_size_t, [c_int, c_int]),
     "ptt_transformer_std_pack_params": (c_int, [c_int, c_int] + [_P] * 11 + [_P, _P]),
     "ptt_transformer_std_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

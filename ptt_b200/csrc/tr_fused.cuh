@@ -35,6 +35,10 @@ struct TrPassArgs {
   int dbg_flags = 0;             // tuning only: 1 = skip the epilogue's global stores, 2 = loader re-reads one weight item
   const float* x_sub = nullptr;  // SOFTMAX, Offset variant: res = x_sub - res   (B*n, ldx)
   int ldx = 0;
+  // STORE_QK, optional rank-1 term: out += row_scalar[pair] * col_vec[channel]  (before the ReLU) -- the similarity
+  // column of TransformerBlockCosine's fc_sim pushed through fc_gamma.0
+  const float* row_scalar = nullptr;   // (pairs)
+  const float* col_vec = nullptr;      // (dm)
 };
 
 bool tr_fused_supported(int n, int k, int dm);

@@ -263,13 +263,25 @@ extern "C" size_t ptt_transformer_block_workspace_bytes(int B, int n, int k, int
   return W.total * sizeof(float);
 }
 
-extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features, int B, int n, int k, int d_points,
-                                         int d_model, int variant, const float* params, const int* knn_idx_or_null,
-                                         float* out, float* attn_or_null, void* workspace, size_t workspace_bytes,
-                                         ptt_stream_t stream) {
+namespace {
+struct TrExtra {
+  const float* q_features = nullptr;   // CrossAttentionBlock: the queries come from these (B, n, d_points) features
+  float divisor = 0.f;                 // softmax temperature; 0 = sqrt(d_model)
+  const float* pair_scalar = nullptr;  // (B, n, k) and (d_model): pre-activation of fc_gamma.0 += pair_scalar * pair_vec
+  const float* pair_vec = nullptr;
+};
+}  // namespace
+
+// variant: bit 0 = Offset (fc2(x - res)), bit 1 = raw (out (B, n, d_model) = the aggregated res; no fc2, no residual)
+static int tr_block_impl(const float* xyz, const float* features, int B, int n, int k, int d_points, int d_model,
+                         int variant_flags, const float* params, const int* knn_idx_or_null, float* out, float* attn_or_null,
+                         void* workspace, size_t workspace_bytes, ptt_stream_t stream, const TrExtra& ex) {
   TrLayout L;
   PTT_CHECK_ARG(B >= 0 && n >= 1 && k >= 1 && k <= n && tr_layout(d_points, d_model, &L));
-  PTT_CHECK_ARG(variant == 0 || variant == 1);
+  PTT_CHECK_ARG(variant_flags >= 0 && variant_flags <= 3);
+  PTT_CHECK_ARG((ex.pair_scalar == nullptr) == (ex.pair_vec == nullptr));
+  const int variant = variant_flags & 1;
+  const bool raw = (variant_flags & 2) != 0;
   if (B == 0) return PTT_OK;
   PTT_CHECK_ARG(xyz && features && params && out);
   TrWorkspace W;
@@ -311,13 +323,24 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
   const bool fused = tr_fused_supported(n, k, dm);
   // fused path, plain variant: fc1 is folded into the projection (x itself is never needed); Offset variant: x is kept
   // for fc2(x - res).  fused: [Wg0.Wq x | Wg0.Wk x | Wv x]; generic path: [q | k | v]
+  if (ex.pair_scalar != nullptr && !fused) return PTT_ERR_UNSUPPORTED;   // the rank-1 term exists in the tcgen05 passes only
   const bool folded = fused && variant == 0;
   if (folded) {
     if ((rc = linear(features, dp, tokens, dp, L.qkg1, 3 * ld, 3 * ld, true, 0, nullptr, 0, qkv, ldq))) return rc;
+    // queries from other features: redo the first ld columns (the weight images are output-block major)
+    if (ex.q_features && (rc = linear(ex.q_features, dp, tokens, dp, L.qkg1, ld, 3 * ld, true, 0, nullptr, 0, qkv, ldq))) return rc;
   } else {
     if ((rc = linear(features, dp, tokens, dp, L.fc1, dm, ld, true, 0, nullptr, 0, x, ld))) return rc;
     if ((rc = linear(x, ld, tokens, dm, fused ? L.qkg : L.qkv, 3 * ld, 3 * ld, false, 0, nullptr, 0, qkv, ldq))) return rc;
+    if (ex.q_features) {
+      if (variant == 1) return PTT_ERR_UNSUPPORTED;      // `res` doubles as the scratch for fc1(q_features); Offset needs x
+      if ((rc = linear(ex.q_features, dp, tokens, dp, L.fc1, dm, ld, true, 0, nullptr, 0, res, ld))) return rc;
+      if ((rc = linear(res, ld, tokens, dm, fused ? L.qkg : L.qkv, ld, 3 * ld, false, 0, nullptr, 0, qkv, ldq))) return rc;
+    }
   }
+  const float divisor = ex.divisor > 0.f ? ex.divisor : sqrtf((float)dm);
+  float* res_out = raw ? out : res;            // raw: the aggregation writes the caller's (B*n, dm) buffer directly
+  const int ld_res = raw ? dm : ld;
 
   if (fused) {
     // ---- pair-row passes on the tensor cores with generated A operands and fused reductions (tr_fused.cu)
@@ -325,7 +348,7 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
     auto img_b = [&](size_t img) { return params + img + (size_t)dm * ld; };         // bias row
     TrPassArgs t;
     t.n = n; t.k = k; t.dm = dm; t.pairs = pairs; t.xyz = xyz; t.knn = knn;
-    t.qkv = qkv; t.ldq = ldq; t.koff = ld; t.voff = 2 * ld; t.divisor = sqrtf((float)dm);
+    t.qkv = qkv; t.ldq = ldq; t.koff = ld; t.voff = 2 * ld; t.divisor = divisor;
     // pass 1: pos = fc_delta.2(relu(fc_delta.0(xyz_i - xyz_j))); what is stored is pos_ij + v_j, the only form in which
     // pos is used again (by the aggregation of pass 3)
     TrPassArgs p1 = t;
@@ -338,13 +361,15 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
     TrPassArgs p2 = t;
     p2.wd0 = params + L.delta0; p2.ldw0 = ld;
     p2.wimg = params + L.wprime; p2.bias = params + L.cprime; p2.relu = 1; p2.out = h; p2.ldo = ld;
+    p2.row_scalar = ex.pair_scalar; p2.col_vec = ex.pair_vec;
     if ((rc = tr_fused_launch(p2, TR_PROD_DELTA0, TR_EPI_STORE_QK, st))) return rc;
     // pass 3: logits = fc_gamma.2(g); softmax over the k neighbours; res = sum p * (v + pos)
     TrPassArgs p3 = t;
     p3.a_src = h; p3.lda = ld; p3.pos = pos; p3.wimg = img_w(L.gamma2); p3.bias = img_b(L.gamma2);
-    p3.out = res; p3.ldo = ld; p3.attn = attn_or_null; p3.pos_has_v = 1;
+    p3.out = res_out; p3.ldo = ld_res; p3.attn = attn_or_null; p3.pos_has_v = 1;
     if (variant == 1) { p3.x_sub = x; p3.ldx = ld; }
     if ((rc = tr_fused_launch(p3, TR_PROD_PLAIN, TR_EPI_SOFTMAX, st))) return rc;
+    if (raw) return PTT_OK;
     return linear(res, ld, tokens, dm, L.fc2, dp, round_up(dp, 4), true, 0, features, dp, out, dp);
   }
   tr_delta0_kernel<<<grid_for(pairs * dm), 256, 0, st>>>(xyz, knn, params + L.delta0, n, k, dm, ld, pairs, h, ld); PTT_LAUNCHED();
@@ -353,8 +378,156 @@ extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features
   if ((rc = linear(a, ld, pairs, dm, L.gamma0, dm, ld, true, 1, nullptr, 0, h, ld))) return rc;
   if ((rc = linear(h, ld, pairs, dm, L.gamma2, dm, ld, true, 0, nullptr, 0, a, ld))) return rc;
   tr_softmax_agg_kernel<<<grid_for(tokens * dm), 256, 0, st>>>(a, pos, ld, qkv, ldq, 2 * ld, knn, n, k, dm,
-                                                                sqrtf((float)dm), tokens, variant == 1 ? x : nullptr, res,
-                                                                ld, attn_or_null); PTT_LAUNCHED();
+                                                                divisor, tokens, variant == 1 ? x : nullptr, res_out,
+                                                                ld_res, attn_or_null); PTT_LAUNCHED();
   if ((rc = ptt_launch_status())) return rc;
+  if (raw) return PTT_OK;
   return linear(res, ld, tokens, dm, L.fc2, dp, round_up(dp, 4), true, 0, features, dp, out, dp);
+}
+
+extern "C" int ptt_transformer_block_fwd(const float* xyz, const float* features, int B, int n, int k, int d_points,
+                                         int d_model, int variant, const float* params, const int* knn_idx_or_null,
+                                         float* out, float* attn_or_null, void* workspace, size_t workspace_bytes,
+                                         ptt_stream_t stream) {
+  PTT_CHECK_ARG(variant == 0 || variant == 1);
+  return tr_block_impl(xyz, features, B, n, k, d_points, d_model, variant, params, knn_idx_or_null, out, attn_or_null,
+                       workspace, workspace_bytes, stream, TrExtra());
+}
+
+extern "C" int ptt_transformer_block_fwd_ex(const float* xyz, const float* features, const float* q_features_or_null, int B,
+                                            int n, int k, int d_points, int d_model, int variant_flags, float divisor_or_0,
+                                            const float* params, const int* knn_idx_or_null,
+                                            const float* pair_scalar_or_null, const float* pair_vec_or_null, float* out,
+                                            float* attn_or_null, void* workspace, size_t workspace_bytes,
+                                            ptt_stream_t stream) {
+  TrExtra ex;
+  ex.q_features = q_features_or_null;
+  ex.divisor = divisor_or_0;
+  ex.pair_scalar = pair_scalar_or_null;
+  ex.pair_vec = pair_vec_or_null;
+  return tr_block_impl(xyz, features, B, n, k, d_points, d_model, variant_flags, params, knn_idx_or_null, out, attn_or_null,
+                       workspace, workspace_bytes, stream, ex);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Small token-level kernels of the secondary registry blocks
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// one warp per token: sim[(b, i), j] = cos(q_i, k_{knn(i, j)})   (F.cosine_similarity, eps 1e-8; variants.py:78-79)
+__global__ void __launch_bounds__(256) pair_cosine_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kk,
+                                                           int ldk, const int* __restrict__ knn, int n, int k, int d,
+                                                           long long tokens, float* __restrict__ sim) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const float eps = 1e-8f;
+  for (long long tok = warp; tok < tokens; tok += nwarps) {
+    const long long b = tok / n;
+    const float* qr = q + tok * ldq;
+    float qq = 0.f;
+    for (int c = lane; c < d; c += 32) { const float v = __ldg(qr + c); qq = fmaf(v, v, qq); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    const float inv_q = 1.f / fmaxf(sqrtf(qq), eps);
+    for (int j = 0; j < k; ++j) {
+      const float* kr = kk + (b * n + __ldg(knn + tok * k + j)) * ldk;
+      float dot = 0.f, k2 = 0.f;
+      for (int c = lane; c < d; c += 32) {
+        const float v = __ldg(kr + c);
+        dot = fmaf(v, __ldg(qr + c), dot);
+        k2 = fmaf(v, v, k2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        k2 += __shfl_xor_sync(0xffffffffu, k2, o);
+      }
+      if (lane == 0) sim[tok * k + j] = (dot * inv_q) * (1.f / fmaxf(sqrtf(k2), eps));
+    }
+  }
+}
+
+// one warp per row: y = LayerNorm(x) * gamma + beta (+ residual); biased variance, two passes over registers-free rows
+__global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, int ldx, long long R, int C,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float eps, const float* __restrict__ residual, int ldr,
+                                                          float* __restrict__ y, int ldy) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = warp; r < R; r += nwarps) {
+    const float* xr = x + r * ldx;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += __ldg(xr + c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float dlt = __ldg(xr + c) - mean; v = fmaf(dlt, dlt, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / (float)C + eps);
+    for (int c = lane; c < C; c += 32) {
+      float o = (__ldg(xr + c) - mean) * rstd;
+      o = o * (gamma ? __ldg(gamma + c) : 1.f) + (beta ? __ldg(beta + c) : 0.f);
+      if (residual) o += __ldg(residual + r * ldr + c);
+      y[r * ldy + c] = o;
+    }
+  }
+}
+
+// one thread per (cloud, channel): p = softmax over the n tokens of logits[b, :, c] / divisor; out = p * other  (variants.py:118-121)
+__global__ void __launch_bounds__(128) token_softmax_gate_kernel(const float* __restrict__ logits, int ldl,
+                                                                  const float* __restrict__ other, int ldo, int n, int C,
+                                                                  float divisor, long long total, float* __restrict__ out,
+                                                                  int ldy, float* __restrict__ attn) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / C;
+    const int c = (int)(e - b * C);
+    const float* lg = logits + b * n * ldl + c;
+    float m = -INFINITY;
+    for (int i = 0; i < n; ++i) m = fmaxf(m, lg[(size_t)i * ldl] / divisor);
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += expf(lg[(size_t)i * ldl] / divisor - m);
+    for (int i = 0; i < n; ++i) {
+      const float p = expf(lg[(size_t)i * ldl] / divisor - m) / s;
+      out[(b * n + i) * ldy + c] = p * __ldg(other + (b * n + i) * ldo + c);
+      if (attn) attn[(b * n + i) * C + c] = p;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int ptt_pair_cosine(const float* q, int ldq, const float* kmat, int ldk, const int* knn, int B, int n, int k,
+                               int d, float* sim, ptt_stream_t stream) {
+  PTT_CHECK_ARG(B >= 0 && n >= 1 && k >= 1 && d >= 1 && ldq >= d && ldk >= d);
+  if (B == 0) return PTT_OK;
+  PTT_CHECK_ARG(q && kmat && knn && sim);
+  const long long tokens = (long long)B * n;
+  pair_cosine_kernel<<<(unsigned)llmin_((tokens + 7) / 8, 148LL * 8), 256, 0, as_stream(stream)>>>(q, ldq, kmat, ldk, knn, n, k, d,
+                                                                                                    tokens, sim); PTT_LAUNCHED();
+  return ptt_launch_status();
+}
+
+extern "C" int ptt_layer_norm_fwd(const float* x, int ldx, int R, int C, const float* gamma, const float* beta, float eps,
+                                  const float* residual_or_null, int ldr, float* y, int ldy, ptt_stream_t stream) {
+  PTT_CHECK_ARG(R >= 0 && C >= 1 && ldx >= C && ldy >= C && (residual_or_null == nullptr || ldr >= C));
+  if (R == 0) return PTT_OK;
+  PTT_CHECK_ARG(x && y);
+  layer_norm_kernel<<<(unsigned)llmin_(((long long)R + 7) / 8, 148LL * 8), 256, 0, as_stream(stream)>>>(
+      x, ldx, R, C, gamma, beta, eps, residual_or_null, ldr, y, ldy); PTT_LAUNCHED();
+  return ptt_launch_status();
+}
+
+extern "C" int ptt_token_softmax_gate(const float* logits, int ldl, const float* other, int ldo, int B, int n, int C,
+                                      float divisor, float* out, int ldy, float* attn_or_null, ptt_stream_t stream) {
+  PTT_CHECK_ARG(B >= 0 && n >= 1 && C >= 1 && ldl >= C && ldo >= C && ldy >= C && divisor > 0.f);
+  if (B == 0) return PTT_OK;
+  PTT_CHECK_ARG(logits && other && out);
+  const long long total = (long long)B * C;
+  token_softmax_gate_kernel<<<(unsigned)llmin_((total + 127) / 128, 148LL * 8), 128, 0, as_stream(stream)>>>(
+      logits, ldl, other, ldo, n, C, divisor, total, out, ldy, attn_or_null); PTT_LAUNCHED();
+  return ptt_launch_status();
 }

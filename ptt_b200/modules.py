@@ -284,6 +284,318 @@ class TransformerBlockSTD(nn.Module):
         return self.fc2(res) + pre, attn
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# The other blocks of transformer_block.__all__.  Same constructors, forward signatures
+# and state_dict keys as the reference classes; in eval / no-grad mode every one of them runs on the kNN vector-attention
+# core (ptt_transformer_block_fwd_ex) or on the token-level kernels, otherwise on the reference's decomposition in torch
+# over our kNN kernel (autograd).
+# ----------------------------------------------------------------------------------------------------------------------
+def _take(points, knn_idx):
+    B, n, k = knn_idx.shape
+    flat = knn_idx.reshape(B, n * k, 1).expand(-1, -1, points.shape[-1])
+    return torch.gather(points, 1, flat).reshape(B, n, k, -1)
+
+
+def _vector_attention(q, kk, v, pos, fc_gamma):
+    attn = fc_gamma(q[:, :, None] - kk + pos)
+    attn = F.softmax(attn / math.sqrt(kk.size(-1)), dim=-2)
+    return torch.einsum("bmnf,bmnf->bmf", attn, v + pos), attn
+
+
+class _PackedModule(nn.Module):
+    """Drops the packed parameter images whenever the parameters may have changed."""
+
+    def __init__(self):
+        super().__init__()
+        self._packed = None
+
+    def train(self, mode=True):
+        self._packed = None
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def _sd(self):
+        return {k: v.detach() for k, v in self.state_dict().items()}
+
+    def _fused(self, *tensors):
+        for t in tensors:
+            if not t.is_cuda:
+                raise ops.PttError("%s runs on CUDA only (there is no CPU path)" % type(self).__name__)
+        return (not self.training) and not (torch.is_grad_enabled() and any(t.requires_grad for t in tensors))
+
+    def _core_layers(self, d_points, d_model, gamma_dim=None):
+        g = gamma_dim or d_model
+        self.fc_delta = nn.Sequential(nn.Linear(3, d_model), nn.ReLU(), nn.Linear(d_model, d_model))
+        self.fc_gamma = nn.Sequential(nn.Linear(g, g), nn.ReLU(), nn.Linear(g, g))
+        self.w_qs = nn.Linear(d_model, d_model, bias=False)
+        self.w_ks = nn.Linear(d_model, d_model, bias=False)
+        self.w_vs = nn.Linear(d_model, d_model, bias=False)
+
+
+def _core_sd(sd, **override):
+    out = {k: sd[k] for k in ops.TRANSFORMER_KEYS if k in sd}
+    out.update(override)
+    return out
+
+
+class TransformerBlockMLP(_PackedModule):
+    """variants.py:211-256: TransformerBlock with two-layer fc1 / fc2."""
+
+    def __init__(self, d_points, d_model, k, **kwargs):
+        super().__init__()
+        self.fc1 = nn.Sequential(nn.Linear(d_points, d_model), nn.ReLU(), nn.Linear(d_model, d_model))
+        self.fc2 = nn.Sequential(nn.Linear(d_model, d_model), nn.ReLU(), nn.Linear(d_model, d_points))
+        self._core_layers(d_points, d_model)
+        self.k = k
+
+    def forward(self, xyz, features):
+        xyz, features = xyz.contiguous(), features.contiguous()
+        B, n, dp = features.shape
+        if self._fused(xyz, features):
+            if self._packed is None:
+                sd = self._sd()
+                core = ops.PackedTransformer(_core_sd(sd, **{"fc1.weight": sd["fc1.2.weight"], "fc1.bias": sd["fc1.2.bias"],
+                                                             "fc2.weight": sd["fc2.0.weight"], "fc2.bias": sd["fc2.0.bias"]}), self.k)
+                self._packed = (ops.PackedLinear(sd["fc1.0.weight"].contiguous(), sd["fc1.0.bias"].contiguous()), core,
+                                ops.PackedLinear(sd["fc2.0.weight"].contiguous(), sd["fc2.0.bias"].contiguous()),
+                                ops.PackedLinear(sd["fc2.2.weight"].contiguous(), sd["fc2.2.bias"].contiguous()))
+            fc1_0, core, fc2_0, fc2_2 = self._packed
+            f2 = features.reshape(B * n, dp)
+            h = fc1_0(f2, relu=True).reshape(B, n, -1)
+            res, attn = ops.transformer_block_fwd_ex(core, xyz, h, flags=2, want_attn=True)
+            out = fc2_2(fc2_0(res.reshape(B * n, -1), relu=True), residual=f2).reshape(B, n, dp)
+            return out, attn
+        knn_idx = ops.knn(xyz.detach(), self.k).long()
+        x = self.fc1(features)
+        res, attn = _vector_attention(self.w_qs(x), _take(self.w_ks(x), knn_idx), _take(self.w_vs(x), knn_idx),
+                                      self.fc_delta(xyz[:, :, None] - _take(xyz, knn_idx)), self.fc_gamma)
+        return self.fc2(res) + features, attn
+
+
+class TransformerBlockCosine(_PackedModule):
+    """variants.py:43-88: the attention input is fc_sim([cos(q_i, k_j) | q_i - k_j]) + pos.  fc_sim and fc_gamma.0 are
+    linear, so the block is the plain core with w_qs / w_ks pre-multiplied by fc_sim's difference columns plus a rank-1
+    term cos(q_i, k_j) * (Wg0 . w_sim) in fc_gamma.0's pre-activation (d_model in {64,128,256,512})."""
+
+    def __init__(self, d_points, d_model, k, **kwargs):
+        super().__init__()
+        self.fc1 = nn.Linear(d_points, d_model)
+        self.fc2 = nn.Linear(d_model, d_points)
+        self._core_layers(d_points, d_model)
+        self.k = k
+        self.fc_sim = nn.Linear(d_model + 1, d_model)
+
+    def forward(self, xyz, features):
+        xyz, features = xyz.contiguous(), features.contiguous()
+        B, n, dp = features.shape
+        if self._fused(xyz, features):
+            if self._packed is None:
+                sd = {k: v.double() for k, v in self._sd().items()}
+                ws, bs = sd["fc_sim.weight"][:, 1:], sd["fc_sim.bias"]
+                wg0 = sd["fc_gamma.0.weight"]
+                f32 = lambda t: t.float().contiguous()
+                core = ops.PackedTransformer(_core_sd(self._sd(), **{
+                    "w_qs.weight": f32(ws @ sd["w_qs.weight"]), "w_ks.weight": f32(ws @ sd["w_ks.weight"]),
+                    "fc_gamma.0.bias": f32(sd["fc_gamma.0.bias"] + wg0 @ bs)}), self.k)
+                lin_q = ops.PackedLinear(f32(sd["w_qs.weight"] @ sd["fc1.weight"]), f32(sd["w_qs.weight"] @ sd["fc1.bias"]))
+                lin_k = ops.PackedLinear(f32(sd["w_ks.weight"] @ sd["fc1.weight"]), f32(sd["w_ks.weight"] @ sd["fc1.bias"]))
+                self._packed = (core, lin_q, lin_k, f32(wg0 @ sd["fc_sim.weight"][:, 0]))
+            core, lin_q, lin_k, vec = self._packed
+            knn_idx = ops.knn(xyz, self.k)
+            f2 = features.reshape(B * n, dp)
+            sim = ops.pair_cosine(lin_q(f2).reshape(B, n, -1), lin_k(f2).reshape(B, n, -1), knn_idx)
+            return ops.transformer_block_fwd_ex(core, xyz, features, knn_idx=knn_idx, pair_scalar=sim, pair_vec=vec,
+                                                want_attn=True)
+        knn_idx = ops.knn(xyz.detach(), self.k).long()
+        x = self.fc1(features)
+        q, kk, v = self.w_qs(x), _take(self.w_ks(x), knn_idx), _take(self.w_vs(x), knn_idx)
+        pos = self.fc_delta(xyz[:, :, None] - _take(xyz, knn_idx))
+        sim = F.cosine_similarity(q.unsqueeze(-2).repeat(1, 1, self.k, 1), kk, dim=-1)
+        rel = self.fc_sim(torch.cat((sim.unsqueeze(-1), q[:, :, None] - kk), dim=-1))
+        attn = F.softmax(self.fc_gamma(rel + pos) / math.sqrt(kk.size(-1)), dim=-2)
+        res = torch.einsum("bmnf,bmnf->bmf", attn, v + pos)
+        return self.fc2(res) + features, attn
+
+
+class TransformerBlockALL(_PackedModule):
+    """variants.py:91-124: no neighbourhoods -- per-token gate, softmax over ALL n tokens of a cloud per channel."""
+
+    def __init__(self, d_points, d_model, k, **kwargs):
+        super().__init__()
+        self.fc1 = nn.Linear(d_points, d_model)
+        self.fc2 = nn.Linear(d_model, d_points)
+        self._core_layers(d_points, d_model)
+        self.k = k
+
+    def forward(self, xyz, features):
+        xyz, features = xyz.contiguous(), features.contiguous()
+        B, n, dp = features.shape
+        if self._fused(xyz, features):
+            if self._packed is None:
+                sd = {k: v.double() for k, v in self._sd().items()}
+                f32 = lambda t: t.float().contiguous()
+                lin = lambda w, b=None: ops.PackedLinear(f32(w), f32(b) if b is not None else None)
+                wd = sd["w_qs.weight"] - sd["w_ks.weight"]
+                self._packed = dict(
+                    qk=lin(wd @ sd["fc1.weight"], wd @ sd["fc1.bias"]),                       # (Wq - Wk) fc1
+                    v=lin(sd["w_vs.weight"] @ sd["fc1.weight"], sd["w_vs.weight"] @ sd["fc1.bias"]),
+                    d0=lin(sd["fc_delta.0.weight"], sd["fc_delta.0.bias"]), d2=lin(sd["fc_delta.2.weight"], sd["fc_delta.2.bias"]),
+                    g0=lin(sd["fc_gamma.0.weight"], sd["fc_gamma.0.bias"]), g2=lin(sd["fc_gamma.2.weight"], sd["fc_gamma.2.bias"]),
+                    fc2=lin(sd["fc2.weight"], sd["fc2.bias"]))
+            P = self._packed
+            f2 = features.reshape(B * n, dp)
+            pos = P["d2"](P["d0"](xyz.reshape(B * n, 3), relu=True))
+            logits = P["g2"](P["g0"](P["qk"](f2, residual=pos), relu=True))
+            dm = logits.shape[1]
+            res, attn = ops.token_softmax_gate(logits.reshape(B, n, dm), P["v"](f2, residual=pos).reshape(B, n, dm),
+                                               math.sqrt(dm), want_attn=True)
+            return P["fc2"](res.reshape(B * n, dm), residual=f2).reshape(B, n, dp), attn
+        x = self.fc1(features)
+        q, kk, v = self.w_qs(x), self.w_ks(x), self.w_vs(x)
+        pos = self.fc_delta(xyz)
+        attn = F.softmax(self.fc_gamma(q - kk + pos) / math.sqrt(kk.size(-1)), dim=-2)
+        return self.fc2(attn * (v + pos)) + features, attn
+
+
+class CrossAttentionBlock(_PackedModule):
+    """variants.py:168-208: queries from the template features, keys / values from the search features (fc2 is defined
+    but unused by the reference; fc3 is the output projection)."""
+
+    def __init__(self, d_points, d_model, k, **kwargs):
+        super().__init__()
+        self.fc1 = nn.Linear(d_points, d_model)
+        self.fc2 = nn.Linear(d_points, d_model)
+        self.fc3 = nn.Linear(d_model, d_points)
+        self._core_layers(d_points, d_model)
+        self.k = k
+
+    def forward(self, xyz, search_feat, template_feat):
+        xyz, search_feat, template_feat = xyz.contiguous(), search_feat.contiguous(), template_feat.contiguous()
+        if self._fused(xyz, search_feat, template_feat):
+            if self._packed is None:
+                sd = self._sd()
+                self._packed = ops.PackedTransformer(_core_sd(sd, **{"fc2.weight": sd["fc3.weight"], "fc2.bias": sd["fc3.bias"]}), self.k)
+            return ops.transformer_block_fwd_ex(self._packed, xyz, search_feat, q_features=template_feat, want_attn=True)
+        knn_idx = ops.knn(xyz.detach(), self.k).long()
+        s, tm = self.fc1(search_feat), self.fc1(template_feat)
+        res, attn = _vector_attention(self.w_qs(tm), _take(self.w_ks(s), knn_idx), _take(self.w_vs(s), knn_idx),
+                                      self.fc_delta(xyz[:, :, None] - _take(xyz, knn_idx)), self.fc_gamma)
+        return self.fc3(res) + search_feat, attn
+
+
+class TransformerBlockBackbone(_PackedModule):
+    """variants.py:259-294: the attention core over EXTERNALLY supplied neighbourhoods (ball-query groups), returning the
+    aggregated d_model features (no fc2, no residual; the reference's debug prints are not reproduced).  The fused path
+    covers the case the arithmetic of the reference admits -- one query per point (features.shape[1] == npoint) with
+    grouped_xyz gathered from new_xyz by grouped_idx; anything else runs on the decomposition."""
+
+    def __init__(self, d_points, d_model, k, **kwargs):
+        super().__init__()
+        self.fc1 = nn.Linear(d_points, d_model)
+        self.fc2 = nn.Linear(d_model, d_points)
+        self._core_layers(d_points, d_model)
+        self.k = k
+
+    def forward(self, new_xyz, grouped_xyz, grouped_idx, features):
+        new_xyz, features = new_xyz.contiguous(), features.contiguous()
+        gx = grouped_xyz.permute(0, 2, 3, 1).contiguous()
+        idx = grouped_idx.long()
+        if self._fused(new_xyz, features) and features.shape[1] == new_xyz.shape[1] and torch.equal(_take(new_xyz, idx), gx):
+            if self._packed is None:
+                self._packed = ops.PackedTransformer(_core_sd(self._sd()), grouped_idx.shape[2])
+            self._packed.k = grouped_idx.shape[2]
+            return ops.transformer_block_fwd_ex(self._packed, new_xyz, features, flags=2, knn_idx=grouped_idx.int().contiguous())
+        x = self.fc1(features)
+        res, _ = _vector_attention(self.w_qs(x), _take(self.w_ks(x), idx), _take(self.w_vs(x), idx),
+                                   self.fc_delta(new_xyz[:, :, None] - gx), self.fc_gamma)
+        return res.contiguous()
+
+
+class MulHeadTransformerLayer(_PackedModule):
+    """multitransformer.py:11-63.  fc_gamma acts on head_dim slices with weights shared by the heads, i.e. it is the
+    block-diagonal d_model x d_model map diag(Wg, ..., Wg): the layer is the plain core with those weights and the
+    temperature sqrt(head_dim), followed by proj -> LayerNorm -> fc2 -> LayerNorm -> + input."""
+
+    def __init__(self, d_points, d_model, k, heads, drop=0.0):
+        super().__init__()
+        self.heads = heads
+        head_dim = d_model // heads
+        self.fc1 = nn.Linear(d_points, d_model)
+        self.fc2 = nn.Linear(d_model, d_points)
+        self._core_layers(d_points, d_model, gamma_dim=head_dim)
+        self.proj = nn.Linear(d_model, d_model, bias=False)
+        self.proj_drop = nn.Dropout(drop)
+        self.k = k
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_points)
+
+    def forward(self, xyz, features):
+        xyz, features = xyz.contiguous(), features.contiguous()
+        B, n, dp = features.shape
+        H = self.heads
+        if self._fused(xyz, features):
+            if self._packed is None:
+                sd = self._sd()
+                bd = lambda w: torch.block_diag(*([w] * H)).contiguous()
+                core = ops.PackedTransformer(_core_sd(sd, **{
+                    "fc_gamma.0.weight": bd(sd["fc_gamma.0.weight"]), "fc_gamma.0.bias": sd["fc_gamma.0.bias"].repeat(H).contiguous(),
+                    "fc_gamma.2.weight": bd(sd["fc_gamma.2.weight"]), "fc_gamma.2.bias": sd["fc_gamma.2.bias"].repeat(H).contiguous()}),
+                    self.k)
+                self._packed = (core, ops.PackedLinear(sd["proj.weight"].contiguous()),
+                                ops.PackedLinear(sd["fc2.weight"].contiguous(), sd["fc2.bias"].contiguous()))
+            core, proj, fc2 = self._packed
+            dm = core.d_model
+            res, attn = ops.transformer_block_fwd_ex(core, xyz, features, flags=2, divisor=math.sqrt(dm // H), want_attn=True)
+            y = ops.layer_norm(proj(res.reshape(B * n, dm)), self.norm1.weight.detach(), self.norm1.bias.detach(), self.norm1.eps)
+            y = ops.layer_norm(fc2(y), self.norm2.weight.detach(), self.norm2.bias.detach(), self.norm2.eps,
+                               residual=features.reshape(B * n, dp))
+            attn = attn.view(B, n, self.k, H, dm // H).permute(0, 3, 1, 2, 4).flatten(0, 1)     # the reference's (B*H, n, k, head_dim)
+            return y.reshape(B, n, dp), attn
+        knn_idx = ops.knn(xyz.detach(), self.k).long()
+        x = self.fc1(features)
+        C = x.shape[2]
+        query = self.w_qs(x).view(B, n, H, -1).permute(0, 2, 1, 3).flatten(0, 1)
+        split = lambda t: t.view(B, n, t.shape[2], H, -1).permute(0, 3, 1, 2, 4).flatten(0, 1)
+        pos, key, value = map(split, (self.fc_delta(xyz[:, :, None] - _take(xyz, knn_idx)), _take(self.w_ks(x), knn_idx),
+                                      _take(self.w_vs(x), knn_idx)))
+        res, attn = _vector_attention(query, key, value, pos, self.fc_gamma)
+        if H > 1:
+            res = res.permute(0, 2, 1).reshape(B, C, n).permute(0, 2, 1)
+        res = self.norm1(self.proj_drop(self.proj(res)))
+        return self.norm2(self.fc2(res)) + features, attn
+
+
+class MulTransformerBlock(nn.Module):
+    """multitransformer.py:66-76: `layers` deep copies of one MulHeadTransformerLayer applied in sequence."""
+
+    def __init__(self, d_points, d_model, k, heads, layers):
+        super().__init__()
+        import copy
+        layer = MulHeadTransformerLayer(d_points, d_model, k, heads)
+        self.layers = nn.ModuleList([copy.deepcopy(layer) for _ in range(layers)])
+
+    def forward(self, xyz, features):
+        output, attn = features, None
+        for layer in self.layers:
+            output, attn = layer(xyz, output)
+        return output, attn
+
+
+REGISTRY = {
+    "MulTransformerBlock": MulTransformerBlock, "TransformerBlock": TransformerBlock, "TransformerBlockALL": TransformerBlockALL,
+    "TransformerBlockBackbone": TransformerBlockBackbone, "TransformerBlockCosine": TransformerBlockCosine,
+    "TransformerBlockMLP": TransformerBlockMLP, "TransformerBlockOffset": TransformerBlockOffset,
+    "TransformerBlockSTD": TransformerBlockSTD, "CrossAttentionBlock": CrossAttentionBlock,
+}
+
+
 def register(install_ext=True):
     """Install the B200 modules into the reference's registries (the reference must be importable
     as `ptt`):  pointnet2_modules.PointnetSAModuleVotes (looked up at construction time by
@@ -296,7 +608,6 @@ def register(install_ext=True):
     from ptt.models import transformer_block
 
     pointnet2_modules.PointnetSAModuleVotes = PointnetSAModuleVotes
-    transformer_block.__all__["TransformerBlock"] = TransformerBlock
-    transformer_block.__all__["TransformerBlockOffset"] = TransformerBlockOffset
-    transformer_block.__all__["TransformerBlockSTD"] = TransformerBlockSTD
+    for name, cls in REGISTRY.items():          # every name of transformer_block/__init__.py:7-17
+        transformer_block.__all__[name] = cls
     return pointnet2_modules, transformer_block

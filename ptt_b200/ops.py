@@ -465,6 +465,70 @@ def transformer_block_fwd(packed, xyz, features, knn_idx=None, want_attn=False, 
     return (out, attn) if want_attn else out
 
 
+def transformer_block_fwd_ex(packed, xyz, features, q_features=None, flags=0, divisor=0.0, knn_idx=None, pair_scalar=None,
+                             pair_vec=None, want_attn=False, workspace=None):
+    """ptt_transformer_block_fwd_ex: flags bit 0 = Offset, bit 1 = raw (returns res (B,n,d_model))."""
+    _req(xyz, _F, 3, "xyz"), _req(features, _F, 3, "features")
+    dev = _same_device(xyz, features, knn_idx, q_features, pair_scalar, pair_vec)
+    B, n, _ = xyz.shape
+    if tuple(features.shape) != (B, n, packed.d_points):
+        raise PttError("transformer_block_fwd_ex: features must be (B,n,%d)" % packed.d_points)
+    if q_features is not None and tuple(_req(q_features, _F, 3, "q_features").shape) != tuple(features.shape):
+        raise PttError("transformer_block_fwd_ex: q_features must have the shape of features")
+    if knn_idx is not None:
+        _req(knn_idx, _I, 3, "knn_idx")
+    if (pair_scalar is None) != (pair_vec is None):
+        raise PttError("transformer_block_fwd_ex: pair_scalar and pair_vec come together")
+    if pair_scalar is not None:
+        _req(pair_scalar, _F, 3, "pair_scalar"), _req(pair_vec, _F, 1, "pair_vec")
+    L = _lib.lib()
+    with _DeviceGuard(dev):
+        out = torch.empty(B, n, packed.d_model if flags & 2 else packed.d_points, dtype=_F, device=dev)
+        attn = torch.empty(B, n, packed.k, packed.d_model, dtype=_F, device=dev) if want_attn else None
+        ws = workspace if workspace is not None else _workspace(packed.workspace_bytes(B, n), dev)
+        check(L.ptt_transformer_block_fwd_ex(_ptr(xyz), _ptr(features), _ptr(q_features), B, n, packed.k, packed.d_points,
+                                             packed.d_model, int(flags), float(divisor), _ptr(packed.params), _ptr(knn_idx),
+                                             _ptr(pair_scalar), _ptr(pair_vec), _ptr(out), _ptr(attn), _ptr(ws),
+                                             ws.numel() * 4, _stream()), "ptt_transformer_block_fwd_ex")
+    return (out, attn) if want_attn else out
+
+
+def pair_cosine(q, kmat, knn_idx):
+    """q, kmat (B,n,d), knn_idx (B,n,k) int32 -> (B,n,k) cosine similarities."""
+    _req(q, _F, 3, "q"), _req(kmat, _F, 3, "kmat"), _req(knn_idx, _I, 3, "knn_idx")
+    dev = _same_device(q, kmat, knn_idx)
+    B, n, d = q.shape
+    k = knn_idx.shape[2]
+    with _DeviceGuard(dev):
+        sim = torch.empty(B, n, k, dtype=_F, device=dev)
+        check(_lib.lib().ptt_pair_cosine(_ptr(q), d, _ptr(kmat), kmat.shape[2], _ptr(knn_idx), B, n, k, d, _ptr(sim), _stream()),
+              "ptt_pair_cosine")
+    return sim
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, residual=None):
+    """x (R,C) -> LayerNorm over C (* gamma + beta) (+ residual (R,C))."""
+    _req(x, _F, 2, "x")
+    R, C = x.shape
+    with _DeviceGuard(x.device):
+        y = torch.empty_like(x)
+        check(_lib.lib().ptt_layer_norm_fwd(_ptr(x), C, R, C, _ptr(gamma), _ptr(beta), float(eps), _ptr(residual),
+                                            C if residual is not None else 0, _ptr(y), C, _stream()), "ptt_layer_norm_fwd")
+    return y
+
+
+def token_softmax_gate(logits, other, divisor, want_attn=False):
+    """logits, other (B,n,C): softmax over the n tokens per (cloud, channel), times other."""
+    _req(logits, _F, 3, "logits"), _req(other, _F, 3, "other")
+    B, n, C = logits.shape
+    with _DeviceGuard(logits.device):
+        out = torch.empty_like(logits)
+        attn = torch.empty_like(logits) if want_attn else None
+        check(_lib.lib().ptt_token_softmax_gate(_ptr(logits), C, _ptr(other), C, B, n, C, float(divisor), _ptr(out), C,
+                                                _ptr(attn), _stream()), "ptt_token_softmax_gate")
+    return (out, attn) if want_attn else out
+
+
 STD_KEYS = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc_delta.0.weight", "fc_delta.0.bias",
             "fc_delta.2.weight", "fc_delta.2.bias", "w_qs.weight", "w_ks.weight", "w_vs.weight")
 

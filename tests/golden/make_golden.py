@@ -116,6 +116,30 @@ def transformer_fixture(models):
         out[name + "/features_crc"] = np.uint32(synth.crc(feats))
         out[name + "/res"] = res
         out[name + "/attn_head"] = attn[:, :4].contiguous()   # the first 4 tokens only (size)
+    # the other registered blocks (transformer_block/__init__.py:7-17), built through the reference's own classes
+    from ptt.models.transformer_block import multitransformer
+    extra = {
+        # name: (class, n, d_points, d_model, k, heads, layers)
+        "cosine": ("TransformerBlockCosine", 48, 32, 64, 8, 1, 1),
+        "all": ("TransformerBlockALL", 40, 24, 48, 4, 1, 1),
+        "cross": ("CrossAttentionBlock", 48, 32, 64, 8, 1, 1),
+        "mul": ("MulTransformerBlock", 48, 32, 64, 8, 4, 2),
+    }
+    for i, (name, (cls, n, dp, dm, k, heads, layers)) in enumerate(extra.items()):
+        ctor = multitransformer.MulTransformerBlock if cls == "MulTransformerBlock" else getattr(variants, cls)
+        mod = ctor(d_points=dp, d_model=dm, k=k, heads=heads, layers=layers).eval()
+        synth.load_filled(mod, seed=80 + i)
+        xyz = synth.make_clouds(2, n, 90 + i, "dense", role="template")
+        feats = synth.features((2, n, dp), seed=100 + i)
+        if cls == "CrossAttentionBlock":
+            feats2 = synth.features((2, n, dp), seed=110 + i)
+            res, attn = mod(t(xyz), t(feats), t(feats2))
+        else:
+            res, attn = mod(t(xyz), t(feats))
+        out[name + "/xyz"] = xyz
+        out[name + "/features_crc"] = np.uint32(synth.crc(feats))
+        out[name + "/res"] = res
+        out[name + "/attn_head"] = attn[:, :4].contiguous()
     save("transformer.npz", **out)
 
 

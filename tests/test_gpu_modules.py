@@ -349,3 +349,78 @@ def test_full_model_sparse_and_small_vs_port():
     out = hp.forward_full(g(search), g(template))
     torch.cuda.synchronize()
     _check_full(out, torch_port.full_model_frame(sd, t(search), t(template), cfg), sd, cfg)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# a10 / N4: the other blocks of transformer_block.__all__
+# ------------------------------------------------------------------------------------------------------------------
+from test_oracle_golden import EXTRA_TR_CASES, extra_transformer_state_dict, run_extra_port  # noqa: E402
+
+
+def _build_extra(cls, dp, dm, k, heads, layers, sd):
+    mod = modules.REGISTRY[cls](d_points=dp, d_model=dm, k=k, heads=heads, layers=layers)
+    mod.load_state_dict(sd)
+    return mod.to(DEV).eval()
+
+
+@pytest.mark.parametrize("name", list(EXTRA_TR_CASES))
+def test_secondary_blocks_vs_reference_fixture(golden, name):
+    gd = golden("transformer.npz")
+    i = list(EXTRA_TR_CASES).index(name)
+    cls, n, dp, dm, k, heads, layers = EXTRA_TR_CASES[name]
+    sd = filled(extra_transformer_state_dict(cls, dp, dm, heads, layers), 80 + i)
+    mod = _build_extra(cls, dp, dm, k, heads, layers, sd)
+    f = synth.features((2, n, dp), seed=100 + i)
+    args = [g(gd[name + "/xyz"]), g(f)]
+    if cls == "CrossAttentionBlock":
+        args.append(g(synth.features((2, n, dp), seed=110 + i)))
+    with torch.no_grad():
+        res, attn = mod(*args)
+    np.testing.assert_allclose(res.cpu().numpy(), gd[name + "/res"], **FP_TOL)
+    np.testing.assert_allclose(attn[:, :4].cpu().numpy(), gd[name + "/attn_head"], **FP_TOL)
+
+
+@pytest.mark.parametrize("case", [("TransformerBlockCosine", 3, 128, 256, 512, 16, 1, 1), ("TransformerBlockCosine", 2, 50, 64, 128, 4, 1, 1),
+                                  ("CrossAttentionBlock", 3, 64, 256, 512, 16, 1, 1), ("MulTransformerBlock", 2, 128, 256, 512, 16, 8, 1),
+                                  ("MulTransformerBlock", 2, 40, 32, 256, 8, 1, 2), ("TransformerBlockALL", 3, 128, 256, 512, 16, 1, 1),
+                                  ("TransformerBlockALL", 2, 33, 20, 40, 3, 1, 1), ("CrossAttentionBlock", 2, 30, 24, 40, 5, 1, 1)])
+def test_secondary_blocks_vs_port(case):
+    """The production sizes (d_model 512: CTA-pair tcgen05 passes) and ragged / generic-path sizes against the port."""
+    cls, B, n, dp, dm, k, heads, layers = case
+    sd = filled(extra_transformer_state_dict(cls, dp, dm, heads, layers), 200 + n)
+    mod = _build_extra(cls, dp, dm, k, heads, layers, sd)
+    xyz = synth.make_clouds(B, n, 300 + n, "dense", role="template")
+    f = synth.features((B, n, dp), seed=310 + n)
+    f2 = synth.features((B, n, dp), seed=320 + n) if cls == "CrossAttentionBlock" else None
+    with torch.no_grad():
+        res, attn = mod(*([g(xyz), g(f)] + ([g(f2)] if f2 is not None else [])))
+    want_res, want_attn = run_extra_port(cls, sd, t(xyz), t(f), k, heads, t(f2) if f2 is not None else None)
+    np.testing.assert_allclose(res.cpu().numpy(), want_res.numpy(), **FP_TOL)
+    np.testing.assert_allclose(attn.cpu().numpy(), want_attn.numpy(), **FP_TOL)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 256, 512, 16), (2, 32, 32, 64, 8)])
+def test_mlp_and_backbone_blocks_vs_port(shape):
+    B, n, dp, dm, k = shape
+    sd = filled(transformer_state_dict("TransformerBlockMLP", dp, dm), 400 + n)
+    mod = modules.TransformerBlockMLP(dp, dm, k)
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV).eval()
+    xyz = synth.make_clouds(B, n, 410 + n, "dense", role="template")
+    f = synth.features((B, n, dp), seed=420 + n)
+    with torch.no_grad():
+        res, attn = mod(g(xyz), g(f))
+    want_res, want_attn = torch_port.transformer_block(sd, t(xyz), t(f), k, variant="TransformerBlockMLP")
+    np.testing.assert_allclose(res.cpu().numpy(), want_res.numpy(), **FP_TOL)
+    np.testing.assert_allclose(attn.cpu().numpy(), want_attn.numpy(), **FP_TOL)
+    # Backbone: neighbourhoods supplied by the caller (here: a ball query over the points themselves)
+    sd = filled(transformer_state_dict("TransformerBlock", dp, dm), 430 + n)
+    bb = modules.TransformerBlockBackbone(dp, dm, k)
+    bb.load_state_dict(sd)
+    bb = bb.to(DEV).eval()
+    idx = cops.ball_query(t(xyz), t(xyz), 0.6, k)
+    grouped = cops.group_points(t(xyz).transpose(1, 2).contiguous(), idx)
+    with torch.no_grad():
+        got = bb(g(xyz), g(grouped), g(idx), g(f))
+    want = torch_port.transformer_block_backbone(sd, t(xyz), grouped, idx, t(f))
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), **FP_TOL)

@@ -174,3 +174,53 @@ def test_port_full_model_vs_reference_fixture(golden):
     np.testing.assert_allclose(out["pred_box_center"].numpy(), g["full/pred_box_center"], rtol=1e-5, atol=1e-4)
     for k in FULL_KEYS:
         np.testing.assert_allclose(out[k].numpy(), g["full/" + k], err_msg=k, **FP_TOL)
+
+
+# the other registered blocks: name -> (class, n, d_points, d_model, k, heads, layers); fixtures made by make_golden.py
+EXTRA_TR_CASES = {
+    "cosine": ("TransformerBlockCosine", 48, 32, 64, 8, 1, 1),
+    "all": ("TransformerBlockALL", 40, 24, 48, 4, 1, 1),
+    "cross": ("CrossAttentionBlock", 48, 32, 64, 8, 1, 1),
+    "mul": ("MulTransformerBlock", 48, 32, 64, 8, 4, 2),
+}
+
+
+def extra_transformer_state_dict(cls, dp, dm, heads=1, layers=1):
+    """state_dict layout (key -> shape) of the secondary blocks (variants.py:43-124,168-208; multitransformer.py:11-76)."""
+    if cls == "MulTransformerBlock":
+        hd = dm // heads
+        one = transformer_state_dict("TransformerBlock", dp, dm)
+        for nm in ("fc_gamma.0", "fc_gamma.2"):
+            one[nm + ".weight"], one[nm + ".bias"] = (hd, hd), (hd,)
+        one.update({"proj.weight": (dm, dm), "norm1.weight": (dm,), "norm1.bias": (dm,), "norm2.weight": (dp,), "norm2.bias": (dp,)})
+        return {"layers.%d.%s" % (i, k): v for i in range(layers) for k, v in one.items()}
+    sd = transformer_state_dict("TransformerBlock", dp, dm)
+    if cls == "TransformerBlockCosine":
+        sd.update({"fc_sim.weight": (dm, dm + 1), "fc_sim.bias": (dm,)})
+    if cls == "CrossAttentionBlock":
+        sd.update({"fc2.weight": (dm, dp), "fc2.bias": (dm,), "fc3.weight": (dp, dm), "fc3.bias": (dp,)})
+    return sd
+
+
+def run_extra_port(cls, sd, xyz, feats, k, heads, feats2=None):
+    if cls == "TransformerBlockCosine":
+        return torch_port.transformer_block_cosine(sd, xyz, feats, k)
+    if cls == "TransformerBlockALL":
+        return torch_port.transformer_block_all(sd, xyz, feats)
+    if cls == "CrossAttentionBlock":
+        return torch_port.cross_attention_block(sd, xyz, feats, feats2, k)
+    return torch_port.mul_transformer_block(sd, xyz, feats, k, heads)
+
+
+@pytest.mark.parametrize("name", list(EXTRA_TR_CASES))
+def test_port_secondary_blocks_vs_reference_fixture(golden, name):
+    g = golden("transformer.npz")
+    i = list(EXTRA_TR_CASES).index(name)
+    cls, n, dp, dm, k, heads, layers = EXTRA_TR_CASES[name]
+    sd = {kk: t(v) for kk, v in synth.fill_state_dict(extra_transformer_state_dict(cls, dp, dm, heads, layers), seed=80 + i).items()}
+    f = synth.features((2, n, dp), seed=100 + i)
+    assert synth.crc(f) == int(g[name + "/features_crc"])
+    f2 = t(synth.features((2, n, dp), seed=110 + i)) if cls == "CrossAttentionBlock" else None
+    res, attn = run_extra_port(cls, sd, t(g[name + "/xyz"]), t(f), k, heads, f2)
+    np.testing.assert_allclose(res.numpy(), g[name + "/res"], **FP_TOL)
+    np.testing.assert_allclose(attn[:, :4].numpy(), g[name + "/attn_head"], **FP_TOL)
