@@ -44,8 +44,8 @@ struct SfCfg {
   static constexpr uint32_t RING_BYTES = SF_NS * SF_STAGE_BYTES;
   static constexpr uint32_t CTRL_BYTES = 256 + 128 * 16 + (SH2_SMEM ? D2 * 4 : 0);
   static constexpr uint32_t SMEM_BYTES = HA_BYTES + HB_BYTES + RING_BYTES + CTRL_BYTES;   // 231,680 B at (256,256,256); limit 232,448
-  static constexpr uint32_t D2_COL = 0, D3_COL = D2 < 128 ? 128 : D2, TMEM_COLS = 512;
-  static_assert(D3_COL + D3 <= 512, "accumulators exceed TMEM");
+  static constexpr uint32_t D2_COL = 0, D3_COL = D2 < 128 ? 128 : D2, TMEM_COLS = 512;   // D3^T: ITEMS3 blocks of 128 columns
+  static_assert(D3_COL + ITEMS3 * 128 <= 512, "accumulators exceed TMEM");
 };
 
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -64,6 +64,27 @@ __device__ __forceinline__ void sf_load_item(uint8_t* dst, const uint8_t* img, i
     }
   } else {
     tc::bulk_g2s(dst, img + (size_t)(ni * KB + kb) * 16384, 16384, bar);
+  }
+}
+
+// E3 of one 32-row block held by one thread (its output channel): max over every group of NSW consecutive rows, then
+// shift + ReLU and the store to (centre, channel).  dst = the block's first centre; groups wider than the block (ns > 32)
+// are combined through the zero-initialised output with atomicMax (values are >= +0, so unsigned order == float order).
+template <int NSW>
+__device__ __forceinline__ void sf_store_groups(float (&v)[32], long long R0, long long rows, float shift, float* dst, int ld_out,
+                                                bool atomic) {
+#pragma unroll
+  for (int o = 1; o < NSW; o <<= 1)
+#pragma unroll
+    for (int j = 0; j < 32; j += 2 * o) v[j] = fmaxf(v[j], v[j + o]);
+#pragma unroll
+  for (int g = 0; g < 32 / NSW; ++g) {
+    if (R0 + g * NSW < rows) {
+      const float y = fmaxf(v[g * NSW] + shift, 0.f);
+      float* p = dst + (long long)g * ld_out;
+      if (atomic) atomicMax(reinterpret_cast<unsigned int*>(p), __float_as_uint(y));
+      else *p = y;
+    }
   }
 }
 
@@ -121,7 +142,14 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     const int quarter = warp & 3, half = warp >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const unsigned gmask = ns >= 32 ? 0xffffffffu : (((1u << ns) - 1u) << (lane & ~(ns - 1)));
+    // E3 ownership: this warp's 32 lanes are 32 consecutive output channels of one 128-channel block of layer 3
+    static_assert(Cfg::NI3 == 128 && (Cfg::ITEMS3 == 1 || Cfg::ITEMS3 == 2), "layer 3 is issued transposed in 128-channel blocks");
+    constexpr int E3_BLOCKS = Cfg::ITEMS3 == 2 ? 4 : 2;    // 32-row column groups handled by this warp per tile
+    const int e3_mb = Cfg::ITEMS3 == 2 ? half : 0;
+    const int e3_ch = e3_mb * 128 + quarter * 32 + lane;
+    const float e3_shift = __ldg(a.shift3 + e3_ch);
+    const int nsw = ns < 32 ? ns : 32;
+    const int log2ns = 31 - __clz(ns);
     int it = 0;
     int sb = 0;                 // H2 ring slot
     uint32_t pb = 0;            // its phase
@@ -173,34 +201,24 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       tc::mbar_wait(d3_full, par);
       tc::tc_fence_after();
       if (erec) a.dbg[1000 + it * 4 + 2] = clock64();
-      const long long R = (long long)tile * SF_TM + r;
-      const bool writer = (lane & (ns - 1)) == 0 && R < a.rows;
-      float* orow = a.out_pm + (R / ns) * (long long)a.ld_out;
+      // Layer 3 is computed TRANSPOSED (D3^T = W3' . H2^T: output channels in the TMEM lanes, the tile's 128 pair-rows in
+      // the columns), so the max over a centre's ns rows runs along the registers of ONE thread -- no shuffles, no warp
+      // reductions -- and the 32 lanes of a warp write 32 consecutive channels of a centre (one coalesced 128-byte store).
+      // shift + ReLU commute with the max and are applied to the survivors only.
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < D3; c0 += 64) {
+      for (int blk = 0; blk < E3_BLOCKS; ++blk) {
+        const int cg = Cfg::ITEMS3 == 2 ? blk : half * 2 + blk;        // 32-row column group of the tile
         float v[32];
-        tc::tmem_ld32(lane_addr + Cfg::D3_COL + (uint32_t)c0, v);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift3 + c0 + j));
-          const float s4[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float y = v[j + u] + s4[u];
-            y = y > 0.f ? y : 0.f;                             // ReLU; exactly +0 so that uint order == float order
-            v[j + u] = __uint_as_float(__reduce_max_sync(gmask, __float_as_uint(y)));
-          }
-        }
-        if (writer) {
-          if (ns <= 32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            // a group spans several warps: combine through the (zero-initialised) output; values are >= +0 after the
-            // ReLU, so unsigned order == float order
-#pragma unroll
-            for (int j = 0; j < 32; ++j) atomicMax(reinterpret_cast<unsigned int*>(orow + c0 + j), __float_as_uint(v[j]));
-          }
+        tc::tmem_ld32(lane_addr + Cfg::D3_COL + (uint32_t)(e3_mb * SF_TM + cg * 32), v);
+        const long long R0 = (long long)tile * SF_TM + cg * 32;          // first pair-row of this block
+        float* dst = a.out_pm + (R0 >> log2ns) * (long long)a.ld_out + e3_ch;
+        switch (nsw) {                                                   // uniform: straight-line code per group width
+          case 32: sf_store_groups<32>(v, R0, a.rows, e3_shift, dst, a.ld_out, ns > 32); break;
+          case 16: sf_store_groups<16>(v, R0, a.rows, e3_shift, dst, a.ld_out, false); break;
+          case 8: sf_store_groups<8>(v, R0, a.rows, e3_shift, dst, a.ld_out, false); break;
+          case 4: sf_store_groups<4>(v, R0, a.rows, e3_shift, dst, a.ld_out, false); break;
+          case 2: sf_store_groups<2>(v, R0, a.rows, e3_shift, dst, a.ld_out, false); break;
+          default: sf_store_groups<1>(v, R0, a.rows, e3_shift, dst, a.ld_out, false); break;
         }
       }
       tc::tc_fence_before();
@@ -234,7 +252,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       return info;
     };
     // layer-1 xyz weights of this thread's channels: kept in registers for up to two k-blocks, re-read (L1) beyond
-    constexpr bool HOIST = Cfg::KB1 <= 2;
+    constexpr bool HOIST = Cfg::KB1 <= 1;   // beyond one k-block the registers go to the gather prefetch instead
     constexpr int HK = HOIST ? Cfg::KB1 : 1;
     float wxr[HK][3][4], g0r[HK][4];
     if (HOIST) {
@@ -263,6 +281,19 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       const int idx_nn = row_index(tile + 2 * stride);
       const bool prec = a.dbg != nullptr && blockIdx.x == 0 && pt == 0 && it < 30;
       if (prec) a.dbg[2000 + it * 3 + 0] = clock64();
+      // The G' rows of a k-block (8 rows per thread, dependent on s_info) are all in flight at once, and those of
+      // k-block h+1 are requested before k-block h is converted: one exposed gather latency per tile instead of 2 KB1.
+      auto gather = [&](int h, float4 (&dst)[8]) {
+        const int c = h * 64 + q * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int src = __float_as_int(s_info[i * 16 + rsub].w);
+          dst[i] = (a.gprime != nullptr && src >= 0) ? __ldg(reinterpret_cast<const float4*>(a.gprime + (size_t)src * D1 + c))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      float4 gcur[8], gnxt[8];
+      gather(0, gcur);
 #pragma unroll
       for (int h = 0; h < Cfg::KB1; ++h) {
         const int c = h * 64 + q * 4;                   // this thread's 4 channels of k-block h
@@ -273,17 +304,16 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
           for (int d = 0; d < 3; ++d) wx[d][u] = HOIST ? wxr[h < HK ? h : 0][d][u] : __ldg(a.wx + d * D1 + c + u);
           g0[u] = HOIST ? g0r[h < HK ? h : 0][u] : (a.gprime ? 0.f : __ldg(a.shift1 + c + u));
         }
+        if (h + 1 < Cfg::KB1) gather(h + 1, gnxt);
         tc::mbar_wait(&ha_free[sa], pa ^ 1);            // layer 2 has consumed the k-block that used this slot
         if (prec && h == 0) a.dbg[2000 + it * 3 + 1] = clock64();
         uint8_t* blk = HA + sa * SF_KBLOCK_BYTES;
-#pragma unroll 4
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 16 + rsub;
           const float4 info = s_info[r];
           const int src = __float_as_int(info.w);
-          float4 g = make_float4(g0[0], g0[1], g0[2], g0[3]);
-          if (a.gprime != nullptr && src >= 0) g = __ldg(reinterpret_cast<const float4*>(a.gprime + (size_t)src * D1 + c));
-          float y[4] = {g.x, g.y, g.z, g.w};
+          float y[4] = {gcur[i].x + g0[0], gcur[i].y + g0[1], gcur[i].z + g0[2], gcur[i].w + g0[3]};   // g0 = 0 with G'
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             float t = fmaf(wx[0][u], info.x, y[u]);
@@ -301,6 +331,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&ha_full[sa]);
         if (++sa == Cfg::NRA) { sa = 0; pa ^= 1; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gcur[i] = gnxt[i];
       }
       if (prec) a.dbg[2000 + it * 3 + 2] = clock64();
       info_cur = info_nxt;
@@ -332,7 +364,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     // =================================================================== MMA issuer (whole warp, one elected lane issues)
     {
       constexpr uint32_t IDESC2 = tc::idesc_f16<false>(SF_TM, Cfg::NI2);
-      constexpr uint32_t IDESC3 = tc::idesc_f16<false>(SF_TM, Cfg::NI3);
+      constexpr uint32_t IDESC3 = tc::idesc_f16<false>(Cfg::NI3, SF_TM);      // layer 3 transposed: M = channels, N = rows
       int stage = 0;
       uint32_t phase = 0;
       int sa = 0, sb = 0;
@@ -383,11 +415,12 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
           for (int ni = 0; ni < Cfg::ITEMS3; ++ni) {
             tc::mbar_wait(&full_b[stage], phase);
             tc::tc_fence_after();
-            const uint64_t da_hi = tc::smem_desc_sw128(hb_addr + sb * SF_KBLOCK_BYTES);
-            const uint64_t da_lo = tc::smem_desc_sw128(hb_addr + sb * SF_KBLOCK_BYTES + 16384);
-            const uint64_t db_hi = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES);
-            const uint64_t db_lo = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES + Cfg::NI3 * 128);
-            const uint32_t d = tmem_base + Cfg::D3_COL + ni * Cfg::NI3;
+            // transposed: A = the weight item (M = 128 output channels), B = the H2 k-block (N = 128 pair-rows)
+            const uint64_t da_hi = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES);
+            const uint64_t da_lo = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES + Cfg::NI3 * 128);
+            const uint64_t db_hi = tc::smem_desc_sw128(hb_addr + sb * SF_KBLOCK_BYTES);
+            const uint64_t db_lo = tc::smem_desc_sw128(hb_addr + sb * SF_KBLOCK_BYTES + 16384);
+            const uint32_t d = tmem_base + Cfg::D3_COL + ni * SF_TM;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);
