@@ -1,0 +1,57 @@
+"""Trainable twin of the hot path (the training row): the reference's module tree for rows a1-a9 --
+backbone SA1-3 + cov_final (pointnet2_backbone.py:14-50), the two transformer blocks and the box-head SA
+(centroids_voting_head.py:27-28, box_voting_head.py:15-31) -- assembled from ptt_b200.modules with the reference's
+parameter names, so that `state_dict()` keys are those HotPath consumes and a reference checkpoint's hot-path entries
+load by key.  In train() mode every module runs the reference's decomposition over our CUDA ops under autograd
+(BatchNorm batch statistics, gradients as in the reference); under DistributedDataParallel the only collective of a
+step is the gradient all-reduce over NCCL.
+"""
+import torch
+import torch.nn as nn
+
+from . import modules as m
+
+
+class _Backbone(nn.Module):
+    def __init__(self, mlps=((0, 64, 64, 128), (128, 128, 128, 256), (256, 128, 128, 256)), radii=(0.3, 0.5, 0.7),
+                 nsamples=(32, 32, 32), methods=("fps", "sequence", "sequence")):
+        super().__init__()
+        self.SA_modules = nn.ModuleList(
+            m.PointnetSAModuleVotes(mlp=list(mlp), radius=r, nsample=ns, use_xyz=True, normalize_xyz=True, sample_method=meth)
+            for mlp, r, ns, meth in zip(mlps, radii, nsamples, methods))
+        self.cov_final = nn.Conv1d(mlps[-1][-1], 256, kernel_size=1)
+
+    def forward(self, pts, npoints):
+        xyz, feats = pts.contiguous(), None
+        for sa, n in zip(self.SA_modules, npoints):
+            xyz, feats, _ = sa(xyz, feats, n)
+        return xyz, self.cov_final(feats)
+
+
+class _Head(nn.Module):
+    def __init__(self, with_sa):
+        super().__init__()
+        self.transformer_block = m.TransformerBlock(256, 512, 16)
+        if with_sa:
+            self.vote_aggregation = m.PointnetSAModuleVotes(mlp=[257, 256, 256, 256], radius=0.3, nsample=16, use_xyz=True,
+                                                            normalize_xyz=True, sample_method="fps")
+
+
+class HotPathNet(nn.Module):
+    """forward(search (B,Ns,3), template (B,Nt,3)) -> the tensors HotPath.forward returns (same glue between stages)."""
+
+    def __init__(self, npoints_search=(512, 256, 128), npoints_template=(256, 128, 64), box_npoint=64):
+        super().__init__()
+        self.backbone_3d = _Backbone()
+        self.centroid_voting_head = _Head(with_sa=False)
+        self.box_voting_head = _Head(with_sa=True)
+        self.npoints_search, self.npoints_template, self.box_npoint = npoints_search, npoints_template, box_npoint
+
+    def forward(self, search, template):
+        s_xyz, s_feat = self.backbone_3d(search, self.npoints_search)
+        t_xyz, t_feat = self.backbone_3d(template, self.npoints_template)
+        cen, _ = self.centroid_voting_head.transformer_block(s_xyz, s_feat.transpose(1, 2).contiguous())
+        votes_feats = torch.cat([torch.full_like(cen[:, :, :1], 0.5), cen], dim=2).transpose(1, 2).contiguous()
+        b_xyz, b_feat, _ = self.box_voting_head.vote_aggregation(s_xyz, votes_feats, self.box_npoint)
+        box, _ = self.box_voting_head.transformer_block(b_xyz, b_feat.transpose(1, 2).contiguous())
+        return {"search_feats": s_feat, "template_feats": t_feat, "centroid_feats": cen, "box_sa_feats": b_feat, "box_feats": box}

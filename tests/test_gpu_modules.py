@@ -424,3 +424,34 @@ def test_mlp_and_backbone_blocks_vs_port(shape):
         got = bb(g(xyz), g(grouped), g(idx), g(f))
     want = torch_port.transformer_block_backbone(sd, t(xyz), grouped, idx, t(f))
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), **FP_TOL)
+
+
+def test_hot_path_net_state_dict_drives_hotpath_and_trains():
+    """ptt_b200.train.HotPathNet: (a) its state_dict has exactly the hot-path keys, so in eval mode it agrees with
+    HotPath built from the same parameters; (b) one SGD step in train mode gives finite gradients for every parameter."""
+    from ptt_b200 import train
+    net = train.HotPathNet()
+    sd = synth.hot_path_state_dict(0)
+    assert set(net.state_dict().keys()) == set(sd.keys())
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    search, template = g(synth.make_clouds(2, 1024, 950, "dense")), g(synth.make_clouds(2, 512, 951, "dense", role="template"))
+    net.eval()
+    # cov_final is a torch Conv1d here: torch lets cuDNN use TF32 for convolutions by default (1e-3 noise); fp32 for the check
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            got = net(search, template)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    want = hotpath.HotPath(sd, device=DEV)(search, template)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(got["box_feats"].cpu().numpy(), want["box_feats"].cpu().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(got["search_feats"].cpu().numpy(), want["search_feats"].cpu().numpy(), rtol=1e-4, atol=1e-4)
+    net.train()
+    out = net(search, template)
+    loss = sum((v ** 2).mean() for v in out.values())
+    loss.backward()
+    for name, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
