@@ -86,6 +86,25 @@ def algorithmic(a):
     return flops
 
 
+def algorithmic_bytes(a):
+    """Per-frame algorithmic bytes of the index kernels: FPS B*(12N + 4M + 12M for the emitted centres),
+    ball query B*(12N + 12M + 4*M*ns)."""
+    cfgs = scaled_cfg(a) or dict(npoints_search=(512, 256, 128), npoints_template=(256, 128, 64))
+    out = {}
+    for tag, n0, npts in (("search", a.nsearch, cfgs["npoints_search"]), ("template", a.ntemplate, cfgs["npoints_template"])):
+        n = n0
+        for l in range(3):
+            m = npts[l]
+            if l == 0:
+                out["%s.sa1.fps" % tag] = 12.0 * n + 16.0 * m
+            out["%s.sa%d.ball_query" % (tag, l + 1)] = 12.0 * n + 12.0 * m + 4.0 * m * 32
+            n = m
+    ns3 = cfgs["npoints_search"][2]
+    out["box.sa.fps"] = 12.0 * ns3 + 16.0 * 64
+    out["box.sa.ball_query"] = 12.0 * ns3 + 12.0 * 64 + 4.0 * 64 * 16
+    return out
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -352,6 +371,8 @@ def run_b200(a):
         if os.path.exists(pk):
             peaks = json.load(open(pk))
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_gbs = peaks.get("hbm_gbs", 6650.0)
+        abytes = algorithmic_bytes(a)
         achieved_tf = alg[top] * B / (known[top] * 1e-3) / 1e12
         traffic = None
         tp = os.path.join(REPO, "profiles", "r1_traffic.json")     # dram__bytes_read+write per launch from the ncu --set full capture
@@ -377,6 +398,15 @@ def run_b200(a):
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
                          "flops_per_launch": alg[top] * B, "ms_per_launch": known[top]},
             "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
+            # every stage against ITS roofline (same eager pass): dense stages vs the measured bf16 peak (ceiling 1/3, see
+            # frac_ceiling), index kernels vs the measured HBM copy bandwidth (they are latency-bound: serial arg-max chain /
+            # ordered scan over <= 12 KB per cloud, so the HBM fraction is tiny by construction)
+            "stage_roofline": {**{k: {"bound": "tensor", "achieved_tflops": round(alg[k] * B / (v * 1e-3) / 1e12, 1),
+                                      "frac": round(alg[k] * B / (v * 1e-3) / 1e12 / peak_tf, 4)}
+                                  for k, v in sorted(stage_ms.items()) if k in alg},
+                               **{k: {"bound": "hbm", "achieved_gbs": round(abytes[k] * B / (v * 1e-3) / 1e9, 2),
+                                      "frac": round(abytes[k] * B / (v * 1e-3) / 1e9 / peak_gbs, 5)}
+                                  for k, v in sorted(stage_ms.items()) if k in abytes}},
             "launch_mode": "eager" if a.no_graph else "CUDA graph replay (stage_ms / roofline from an eager single-stream pass of the same steps)",
             "wall_ms_per_step_incl_flush": wall_ms / a.steps,
         }

@@ -12,7 +12,7 @@
 namespace {
 
 constexpr int BQ_WARPS = 8;
-constexpr int BQ_CENTRES_PER_CTA = 64;
+constexpr int BQ_CENTRES_PER_CTA = 32;      // 4 centres per warp: enough CTAs to fill the machine at M = 64..512
 constexpr int BQ_MAX_SMEM_POINTS = 16384;  // 192 KB of SoA floats
 
 template <bool STAGED>
@@ -42,21 +42,32 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(const float* 
     const float nx = __ldg(q), ny = __ldg(q + 1), nz = __ldg(q + 2);
     int* row = idx_out + ((size_t)b * M + j) * ns;
     int cnt = 0, first = 0;
-    for (int base = 0; base < N && cnt < ns; base += 32) {
-      const int k = base + lane;
-      bool hit = false;
-      if (k < N) {
-        float x, y, z;
-        if (STAGED) { x = sx[k]; y = sy[k]; z = sz[k]; }
-        else { x = __ldg(P + 3 * k); y = __ldg(P + 3 * k + 1); z = __ldg(P + 3 * k + 2); }
-        hit = sq3(nx - x, ny - y, nz - z) < radius2;
+    // four 32-point chunks per step: their 12 shared-memory loads and 4 ballots are independent, so the scan is not a
+    // chain of load -> test -> ballot latencies; hits are still committed chunk by chunk, in index order
+    for (int base = 0; base < N && cnt < ns; base += 128) {
+      unsigned ballots[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = base + u * 32 + lane;
+        bool hit = false;
+        if (k < N) {
+          float x, y, z;
+          if (STAGED) { x = sx[k]; y = sy[k]; z = sz[k]; }
+          else { x = __ldg(P + 3 * k); y = __ldg(P + 3 * k + 1); z = __ldg(P + 3 * k + 2); }
+          hit = sq3(nx - x, ny - y, nz - z) < radius2;
+        }
+        ballots[u] = __ballot_sync(0xffffffffu, hit);
       }
-      const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-      if (ballot == 0u) continue;
-      if (cnt == 0) first = base + __ffs(ballot) - 1;
-      const int pos = cnt + __popc(ballot & lt_mask);
-      if (hit && pos < ns) row[pos] = k;
-      cnt += __popc(ballot);
+      if ((ballots[0] | ballots[1] | ballots[2] | ballots[3]) == 0u) continue;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned ballot = ballots[u];
+        if (ballot == 0u || cnt >= ns) continue;
+        if (cnt == 0) first = base + u * 32 + __ffs(ballot) - 1;
+        const int pos = cnt + __popc(ballot & lt_mask);
+        if (((ballot >> lane) & 1u) && pos < ns) row[pos] = base + u * 32 + lane;
+        cnt += __popc(ballot);
+      }
     }
     cnt = min(cnt, ns);
     for (int l = cnt + lane; l < ns; l += 32) row[l] = first;  // pad with the first hit; 0 if none

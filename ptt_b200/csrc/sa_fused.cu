@@ -35,7 +35,12 @@ constexpr uint32_t SF_KBLOCK_BYTES = 32768;    // one activation k-block: 128 ro
 template <int D1, int D2, int D3>
 struct SfCfg {
   static constexpr int KB1 = D1 / 64, KB2 = D2 / 64;
-  static constexpr int NRA = KB1 < 2 ? KB1 : 2, NRB = KB2 < 2 ? KB2 : 2;
+  // DEEP (single-k-block layers, i.e. the 64-wide SA1 stack): TWO tiles in flight -- H1 / H2 slots and both accumulators
+  // exist per tile parity, the MMA warp issues layer 2 of tile t+1 BEFORE layer 3 of tile t and the epilogue converts
+  // H2(t+1) BEFORE it reduces D3(t), so none of the per-tile hand-offs (producer -> MMA -> epilogue -> MMA -> epilogue)
+  // sits on the critical path any more.  Wider stacks have neither the shared memory nor the TMEM columns for that.
+  static constexpr bool DEEP = KB1 == 1 && KB2 == 1 && D2 <= 64 && D3 <= 128;
+  static constexpr int NRA = DEEP ? 2 : (KB1 < 2 ? KB1 : 2), NRB = DEEP ? 2 : (KB2 < 2 ? KB2 : 2);
   static constexpr int NI2 = D2 < 128 ? D2 : 128, NI3 = D3 < 128 ? D3 : 128;   // MMA N / rows per weight item
   static constexpr int ITEMS2 = D2 / NI2, ITEMS3 = D3 / NI3;                   // items per k-block
   static constexpr bool SH2_SMEM = D2 < 256;                                    // shift2 staged in shared memory when it fits
@@ -45,7 +50,8 @@ struct SfCfg {
   static constexpr uint32_t CTRL_BYTES = 256 + 128 * 16 + (SH2_SMEM ? D2 * 4 : 0);
   static constexpr uint32_t SMEM_BYTES = HA_BYTES + HB_BYTES + RING_BYTES + CTRL_BYTES;   // 231,680 B at (256,256,256); limit 232,448
   static constexpr uint32_t D2_COL = 0, D3_COL = D2 < 128 ? 128 : D2, TMEM_COLS = 512;   // D3^T: ITEMS3 blocks of 128 columns
-  static_assert(D3_COL + ITEMS3 * 128 <= 512, "accumulators exceed TMEM");
+  static constexpr uint32_t D2_STRIDE = DEEP ? 64 : 0, D3_STRIDE = DEEP ? 128 : 0;       // per tile parity (DEEP)
+  static_assert(D3_COL + ITEMS3 * 128 + D3_STRIDE <= 512 && D2_COL + D2 + D2_STRIDE <= D3_COL, "accumulators exceed TMEM");
 };
 
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -102,9 +108,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
   uint64_t* ha_free = ha_full + Cfg::NRA;                  // [NRA] MMA -> producers
   uint64_t* hb_full = ha_free + Cfg::NRA;                  // [NRB] epilogue -> MMA
   uint64_t* hb_free = hb_full + Cfg::NRB;                  // [NRB] MMA -> epilogue
-  uint64_t* d2_full = hb_free + Cfg::NRB;
-  uint64_t* d3_full = d2_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d3_full + 1);
+  uint64_t* d2_full = hb_free + Cfg::NRB;                  // [2] (one per tile parity; DEEP uses both)
+  uint64_t* d3_full = d2_full + 2;                         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d3_full + 2);
   float4* s_info = reinterpret_cast<float4*>(ctrl + 256);                 // [128] {rel.xyz, point row as int bits}
   float* s_sh2 = reinterpret_cast<float*>(ctrl + 256 + 128 * 16);         // [D2] (shift3 stays in global: E3 is off the critical path)
 
@@ -126,8 +132,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       tc::mbar_init(&hb_full[s], 256);
       tc::mbar_init(&hb_free[s], 1);
     }
-    tc::mbar_init(d2_full, 1);
-    tc::mbar_init(d3_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&d2_full[s], 1);
+      tc::mbar_init(&d3_full[s], 1);
+    }
     tc::mbar_init_fence();
   }
   if (warp == 17) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -150,21 +158,22 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     const float e3_shift = __ldg(a.shift3 + e3_ch);
     const int nsw = ns < 32 ? ns : 32;
     const int log2ns = 31 - __clz(ns);
-    int it = 0;
     int sb = 0;                 // H2 ring slot
     uint32_t pb = 0;            // its phase
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t par = it & 1;
+    // buffer / barrier parity of local tile `it`: DEEP alternates two accumulator sets, otherwise there is one
+    auto e2 = [&](int it, int tile) {
+      const uint32_t p = Cfg::DEEP ? (uint32_t)(it & 1) : 0u, par = Cfg::DEEP ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);
       const bool erec = a.dbg != nullptr && blockIdx.x == 0 && tid == 0 && it < 30;
+      (void)tile;
       // ---- E2: D2 -> H2, one 64-column k-block at a time so that layer 3 can start on the first one
-      tc::mbar_wait(d2_full, par);
+      tc::mbar_wait(&d2_full[p], par);
       tc::tc_fence_after();
       if (erec) a.dbg[1000 + it * 4 + 0] = clock64();
 #pragma unroll 1
       for (int kb = 0; kb < Cfg::KB2; ++kb) {
         const int c0 = kb * 64 + half * 32;
         float v[32];
-        tc::tmem_ld32(lane_addr + Cfg::D2_COL + (uint32_t)c0, v);
+        tc::tmem_ld32(lane_addr + Cfg::D2_COL + p * Cfg::D2_STRIDE + (uint32_t)c0, v);
         tc::mbar_wait(&hb_free[sb], pb ^ 1);            // layer 3 has consumed the k-block that used this slot
         uint8_t* blk = HB + sb * SF_KBLOCK_BYTES;
         const int chunk0 = half * 4;
@@ -197,8 +206,12 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         if (++sb == Cfg::NRB) { sb = 0; pb ^= 1; }
       }
       if (erec) a.dbg[1000 + it * 4 + 1] = clock64();
+    };
+    auto e3 = [&](int it, int tile) {
+      const uint32_t p = Cfg::DEEP ? (uint32_t)(it & 1) : 0u, par = Cfg::DEEP ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);
+      const bool erec = a.dbg != nullptr && blockIdx.x == 0 && tid == 0 && it < 30;
       // ---- E3: D3 -> max over each centre's rows -> out
-      tc::mbar_wait(d3_full, par);
+      tc::mbar_wait(&d3_full[p], par);
       tc::tc_fence_after();
       if (erec) a.dbg[1000 + it * 4 + 2] = clock64();
       // Layer 3 is computed TRANSPOSED (D3^T = W3' . H2^T: output channels in the TMEM lanes, the tile's 128 pair-rows in
@@ -209,7 +222,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       for (int blk = 0; blk < E3_BLOCKS; ++blk) {
         const int cg = Cfg::ITEMS3 == 2 ? blk : half * 2 + blk;        // 32-row column group of the tile
         float v[32];
-        tc::tmem_ld32(lane_addr + Cfg::D3_COL + (uint32_t)(e3_mb * SF_TM + cg * 32), v);
+        tc::tmem_ld32(lane_addr + Cfg::D3_COL + p * Cfg::D3_STRIDE + (uint32_t)(e3_mb * SF_TM + cg * 32), v);
         const long long R0 = (long long)tile * SF_TM + cg * 32;          // first pair-row of this block
         float* dst = a.out_pm + (R0 >> log2ns) * (long long)a.ld_out + e3_ch;
         switch (nsw) {                                                   // uniform: straight-line code per group width
@@ -223,6 +236,21 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       }
       tc::tc_fence_before();
       if (erec) a.dbg[1000 + it * 4 + 3] = clock64();
+    };
+    const int stride = gridDim.x;
+    if (Cfg::DEEP) {
+      if ((int)blockIdx.x < num_tiles) e2(0, blockIdx.x);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += stride, ++it) {
+        if (tile + stride < num_tiles) e2(it + 1, tile + stride);
+        e3(it, tile);
+      }
+    } else {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += stride, ++it) {
+        e2(it, tile);
+        e3(it, tile);
+      }
     }
   } else if (warp < 16) {
     // =================================================================== producers: layer 1 on CUDA cores
@@ -236,20 +264,34 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       if (!(pt < SF_TM && tile < num_tiles && R < a.rows)) return -1;
       return a.idx ? __ldg(a.idx + R) : (int)(R % ns);
     };
-    auto row_info = [&](int tile, int i) -> float4 {
-      float4 info = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    // The loads of a row's point and centre are issued one tile ahead and their values stay RAW in registers until the
+    // top of the next tile: any arithmetic on them here would make the warp wait for the loads it has just issued.
+    struct RowRaw { float px, py, pz, cx, cy, cz; int src; };
+    const int plog2ns = 31 - __clz(ns);
+    auto row_raw = [&](int tile, int i) -> RowRaw {
+      RowRaw w = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, -1};
       if (i >= 0) {
         const long long R = (long long)tile * SF_TM + pt;
-        const long long cj = R / ns;
-        const long long src = (cj / a.M) * a.N + i;
-        if (a.pair_scalar != nullptr) return make_float4(__ldg(a.pair_scalar + R), 0.f, 0.f, __int_as_float((int)src));
-        const float* p = a.xyz + src * 3;
-        const float* c = a.new_xyz + cj * 3;
-        float dx = __fsub_rn(__ldg(p), __ldg(c)), dy = __fsub_rn(__ldg(p + 1), __ldg(c + 1)), dz = __fsub_rn(__ldg(p + 2), __ldg(c + 2));
-        if (a.normalize) { dx = __fdiv_rn(dx, a.radius); dy = __fdiv_rn(dy, a.radius); dz = __fdiv_rn(dz, a.radius); }
-        info = make_float4(dx, dy, dz, __int_as_float((int)src));
+        const int cj = (int)(R >> plog2ns);                 // ns is a power of two here; 32-bit index arithmetic
+        const int src = (cj / a.M) * a.N + i;
+        w.src = src;
+        if (a.pair_scalar != nullptr) {
+          w.px = __ldg(a.pair_scalar + R);
+        } else {
+          const float* p = a.xyz + (long long)src * 3;
+          const float* c = a.new_xyz + (long long)cj * 3;
+          w.px = __ldg(p); w.py = __ldg(p + 1); w.pz = __ldg(p + 2);
+          w.cx = __ldg(c); w.cy = __ldg(c + 1); w.cz = __ldg(c + 2);
+        }
       }
-      return info;
+      return w;
+    };
+    auto row_info = [&](const RowRaw& w) -> float4 {
+      if (w.src < 0) return make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      if (a.pair_scalar != nullptr) return make_float4(w.px, 0.f, 0.f, __int_as_float(w.src));
+      float dx = __fsub_rn(w.px, w.cx), dy = __fsub_rn(w.py, w.cy), dz = __fsub_rn(w.pz, w.cz);
+      if (a.normalize) { dx = __fdiv_rn(dx, a.radius); dy = __fdiv_rn(dy, a.radius); dz = __fdiv_rn(dz, a.radius); }
+      return make_float4(dx, dy, dz, __int_as_float(w.src));
     };
     // layer-1 xyz weights of this thread's channels: kept in registers for up to two k-blocks, re-read (L1) beyond
     constexpr bool HOIST = Cfg::KB1 <= 1;   // beyond one k-block the registers go to the gather prefetch instead
@@ -268,16 +310,16 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     }
     const int stride = gridDim.x;
     int idx_next = row_index(blockIdx.x + stride);              // index for tile t+1
-    float4 info_cur = row_info(blockIdx.x, row_index(blockIdx.x));
+    RowRaw raw_cur = row_raw(blockIdx.x, row_index(blockIdx.x));
     int it = 0;
     int sa = 0;                 // H1 ring slot
     uint32_t pa = 0;            // its phase
     for (int tile = blockIdx.x; tile < num_tiles; tile += stride, ++it) {
       producer_bar();                                   // everyone is done reading s_info of the previous tile
-      if (pt < SF_TM) s_info[pt] = info_cur;
+      if (pt < SF_TM) s_info[pt] = row_info(raw_cur);
       producer_bar();
-      // issue the loads for the next two tiles now; they are consumed after this tile's H1 has been written
-      const float4 info_nxt = row_info(tile + stride, idx_next);
+      // issue the loads for the next two tiles now; they are consumed at the top of the next tile
+      const RowRaw raw_nxt = row_raw(tile + stride, idx_next);
       const int idx_nn = row_index(tile + 2 * stride);
       const bool prec = a.dbg != nullptr && blockIdx.x == 0 && pt == 0 && it < 30;
       if (prec) a.dbg[2000 + it * 3 + 0] = clock64();
@@ -335,7 +377,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         for (int i = 0; i < 8; ++i) gcur[i] = gnxt[i];
       }
       if (prec) a.dbg[2000 + it * 3 + 2] = clock64();
-      info_cur = info_nxt;
+      raw_cur = raw_nxt;
       idx_next = idx_nn;
     }
   } else if (warp == 16) {
@@ -345,18 +387,28 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       uint32_t phase = 0;
       const uint8_t* w2 = static_cast<const uint8_t*>(a.w2img);
       const uint8_t* w3 = static_cast<const uint8_t*>(a.w3img);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      auto load_layer = [&](int layer) {               // all weight items of one layer of one tile, in consumption order
+        const int n_items = layer == 2 ? Cfg::KB1 * Cfg::ITEMS2 : Cfg::KB2 * Cfg::ITEMS3;
 #pragma unroll 1
-        for (int item = 0; item < Cfg::KB1 * Cfg::ITEMS2 + Cfg::KB2 * Cfg::ITEMS3; ++item) {
+        for (int item = 0; item < n_items; ++item) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* dst = ring + stage * SF_STAGE_BYTES;
-          if (item < Cfg::KB1 * Cfg::ITEMS2) {
-            sf_load_item<Cfg::NI2>(dst, w2, Cfg::KB1, item / Cfg::ITEMS2, item % Cfg::ITEMS2, &full_b[stage]);
-          } else {
-            const int j = item - Cfg::KB1 * Cfg::ITEMS2;
-            sf_load_item<Cfg::NI3>(dst, w3, Cfg::KB2, j / Cfg::ITEMS3, j % Cfg::ITEMS3, &full_b[stage]);
-          }
+          if (layer == 2) sf_load_item<Cfg::NI2>(dst, w2, Cfg::KB1, item / Cfg::ITEMS2, item % Cfg::ITEMS2, &full_b[stage]);
+          else sf_load_item<Cfg::NI3>(dst, w3, Cfg::KB2, item / Cfg::ITEMS3, item % Cfg::ITEMS3, &full_b[stage]);
           if (++stage == SF_NS) { stage = 0; phase ^= 1; }
+        }
+      };
+      const int stride = gridDim.x;
+      if (Cfg::DEEP) {                                  // MMA order: G2(0) | G2(t+1), G3(t) | ...
+        if ((int)blockIdx.x < num_tiles) load_layer(2);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += stride) {
+          if (tile + stride < num_tiles) load_layer(2);
+          load_layer(3);
+        }
+      } else {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += stride) {
+          load_layer(2);
+          load_layer(3);
         }
       }
     }
@@ -373,7 +425,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       const bool rec = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
       int nrec = 0;
       auto stamp = [&](int tag) { if (rec && nrec < 300) { a.dbg[2 * nrec] = tag; a.dbg[2 * nrec + 1] = clock64(); ++nrec; } };
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      auto g2 = [&](int it) {
+        const uint32_t p = Cfg::DEEP ? (uint32_t)(it & 1) : 0u;
         // ---- layer 2: D2 = H1 . W2'^T, k-block by k-block as the producers hand H1 over
         stamp(1);
 #pragma unroll 1
@@ -389,7 +442,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
             const uint64_t da_lo = tc::smem_desc_sw128(ha_addr + sa * SF_KBLOCK_BYTES + 16384);
             const uint64_t db_hi = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES);
             const uint64_t db_lo = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES + Cfg::NI2 * 128);
-            const uint32_t d = tmem_base + Cfg::D2_COL + ni * Cfg::NI2;
+            const uint32_t d = tmem_base + Cfg::D2_COL + p * Cfg::D2_STRIDE + ni * Cfg::NI2;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);
@@ -403,8 +456,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
           tc::mma_commit_w(&ha_free[sa]);
           if (++sa == Cfg::NRA) { sa = 0; pa ^= 1; }
         }
-        tc::mma_commit_w(d2_full);
+        tc::mma_commit_w(&d2_full[p]);
         stamp(3);
+      };
+      auto g3 = [&](int it) {
+        const uint32_t p = Cfg::DEEP ? (uint32_t)(it & 1) : 0u;
         // ---- layer 3: D3 = H2 . W3'^T, k-block by k-block as the epilogue hands H2 over
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB2; ++kb) {
@@ -420,7 +476,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
             const uint64_t da_lo = tc::smem_desc_sw128(ring_addr + stage * SF_STAGE_BYTES + Cfg::NI3 * 128);
             const uint64_t db_hi = tc::smem_desc_sw128(hb_addr + sb * SF_KBLOCK_BYTES);
             const uint64_t db_lo = tc::smem_desc_sw128(hb_addr + sb * SF_KBLOCK_BYTES + 16384);
-            const uint32_t d = tmem_base + Cfg::D3_COL + ni * SF_TM;
+            const uint32_t d = tmem_base + Cfg::D3_COL + p * Cfg::D3_STRIDE + ni * SF_TM;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);
@@ -434,8 +490,23 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
           tc::mma_commit_w(&hb_free[sb]);
           if (++sb == Cfg::NRB) { sb = 0; pb ^= 1; }
         }
-        tc::mma_commit_w(d3_full);
+        tc::mma_commit_w(&d3_full[p]);
         stamp(5);
+      };
+      const int stride = gridDim.x;
+      if (Cfg::DEEP) {
+        if ((int)blockIdx.x < num_tiles) g2(0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += stride, ++it) {
+          if (tile + stride < num_tiles) g2(it + 1);
+          g3(it);
+        }
+      } else {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += stride, ++it) {
+          g2(it);
+          g3(it);
+        }
       }
       if (rec) a.dbg[2 * nrec] = -1;
     }
