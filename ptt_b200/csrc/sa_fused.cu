@@ -11,13 +11,16 @@
 // element), and runs layers 2 and 3 on the tensor cores with the fp16 hi/lo split of tc_gemm.cu (3 MMAs per K-step).
 //
 // One CTA per SM, 128 pair-rows (128/ns centres) per tile, static round-robin over tiles.  Warp roles:
-//   warps 0-7   epilogue (warp w: TMEM lane quarter w%4, column half w/4):
-//                 D2 (TMEM) -> +shift, ReLU -> fp16 hi/lo -> HB (smem, UMMA K-major SW128);
-//                 D3 (TMEM) -> +shift, ReLU -> max over each centre's ns rows (redux.sync) -> out (B, M, D3)
-//   warps 8-15  producers: per-row (point index, rel xyz) -> gather G' -> layer 1 -> fp16 hi/lo -> HA (smem)
+//   warps 0-7   epilogue (warp w: TMEM lane quarter w%4, column half / channel block w/4):
+//                 E2: D2 (TMEM, rows in lanes) -> +shift, ReLU -> fp16 hi/lo -> H2 ring slot (smem, UMMA K-major SW128);
+//                 E3: D3^T (TMEM, CHANNELS in lanes: layer 3 is issued transposed) -> max over each centre's ns rows
+//                     along the thread's registers -> +shift, ReLU -> out (B, M, D3), 32 consecutive channels per store
+//   warps 8-15  producers: per-row (point index, rel xyz) -> gather G' -> layer 1 -> fp16 hi/lo -> H1 ring slot
 //   warp  16    weight loader: W2 / W3 as (k-block, <=128 out-channels) items through a 3-stage ring (TMA engine)
-//   warp  17    TMEM allocation + the single thread issuing tcgen05.mma / tcgen05.commit
-// BatchNorm scales of layers 2 and 3 are folded into the packed weights, so both epilogues are acc + shift.
+//   warp  17    TMEM allocation + tcgen05.mma issue (whole warp convergent, one elected lane)
+// H1 / H2 are handed over one k-block at a time through small rings (SfCfg); the single-k-block stack keeps two tiles
+// in flight (SfCfg::DEEP).  BatchNorm scales of layers 2 and 3 are folded into the packed weights, so both epilogues are
+// acc + shift.  The same kernel serves CosineSimAug (pair_scalar, implicit groups of all N points: sa_mlp.cu).
 #include "sa_fused.cuh"
 #include "tc_common.cuh"
 

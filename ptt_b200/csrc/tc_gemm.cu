@@ -94,37 +94,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
   if (warp < 8) {
     // ------------------------------------------------------------ A producers
+    // The 8 row segments of k-block kb+1 are requested before k-block kb is converted, so the global-load latency is
+    // exposed once per CTA instead of once per k-block; full k-blocks take a branch-free path.
     const int c4 = tid & 15;          // float4 column within the 64-wide k block
     const int rsub = tid >> 4;        // 0..15
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = 0; kb < KB; ++kb) {
-      tc::mbar_wait(&empty[stage], phase ^ 1);
-      uint8_t* a_hi = smem + stage * Cfg::STAGE_BYTES;
-      uint8_t* a_lo = a_hi + A_HALF_BYTES;
+    auto load_block = [&](int kb, float4 (&v)[8]) {
       const int k = kb * TBK + c4 * 4;
-      float4 v[8];
+      if ((kb + 1) * TBK <= g.K) {                                   // uniform: the whole k-block lies inside K
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int src = s_row[i * 16 + rsub];
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src >= 0 && k < g.K) {
-          const float* ptr = gx + (size_t)src * g.ldx + k;
-          if (k + 3 < g.K) {
-            v[i] = __ldg(reinterpret_cast<const float4*>(ptr));
-          } else {
-            v[i].x = __ldg(ptr);
-            if (k + 1 < g.K) v[i].y = __ldg(ptr + 1);
-            if (k + 2 < g.K) v[i].z = __ldg(ptr + 2);
+        for (int i = 0; i < 8; ++i) {
+          const int src = s_row[i * 16 + rsub];
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(gx + (size_t)src * g.ldx + k));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int src = s_row[i * 16 + rsub];
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src >= 0 && k < g.K) {
+            const float* ptr = gx + (size_t)src * g.ldx + k;
+            if (k + 3 < g.K) {
+              v[i] = __ldg(reinterpret_cast<const float4*>(ptr));
+            } else {
+              v[i].x = __ldg(ptr);
+              if (k + 1 < g.K) v[i].y = __ldg(ptr + 1);
+              if (k + 2 < g.K) v[i].z = __ldg(ptr + 2);
+            }
           }
         }
       }
+    };
+    float4 cur[8], nxt[8];
+    load_block(0, cur);
+    for (int kb = 0; kb < KB; ++kb) {
+      if (kb + 1 < KB) load_block(kb + 1, nxt);
+      tc::mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* a_hi = smem + stage * Cfg::STAGE_BYTES;
+      uint8_t* a_lo = a_hi + A_HALF_BYTES;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = i * 16 + rsub;
         uint2 ph, pl;
-        tc::split_f16x2(v[i].x, v[i].y, ph.x, pl.x);
-        tc::split_f16x2(v[i].z, v[i].w, ph.y, pl.y);
+        tc::split_f16x2(cur[i].x, cur[i].y, ph.x, pl.x);
+        tc::split_f16x2(cur[i].z, cur[i].w, ph.y, pl.y);
         const uint32_t off = tc::sw128_offset(r, c4 >> 1) + ((c4 & 1) << 3);
         *reinterpret_cast<uint2*>(a_hi + off) = ph;
         *reinterpret_cast<uint2*>(a_lo + off) = pl;
@@ -132,29 +147,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&full_a[stage]);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
     }
   }
-  if (warp < 4) {
-    // ------------------------------------------------------------ epilogue
+  if (warp < 8) {
+    // ------------------------------------------------------------ epilogue: warp w drains TMEM lane quarter w % 4, column
+    // half w / 4 (all eight producer warps take part)
     tc::mbar_wait(accum_full, 0);
     tc::tc_fence_after();
-    const int r = row0 + warp * 32 + lane;
+    const int quarter = warp & 3, chalf = warp >> 2;
+    const int r = row0 + quarter * 32 + lane;
     const bool row_ok = r < g.R;
     const bool vec_y = (g.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(gy) & 15u) == 0);
     const bool vec_r = gres && (g.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(gres) & 15u) == 0);
+    constexpr int CH = BN >= 64 ? BN / 2 : BN;          // columns per warp
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = chalf * CH; c0 < chalf * CH + CH; c0 += 32) {
       const int col0 = ntile * BN + c0;
       if (col0 >= g.N) break;       // warp-uniform
       float v[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
       if (!row_ok) continue;
       float* yrow = gy + (size_t)r * g.ldy + col0;
       const float* rrow = gres ? gres + (size_t)r * g.ldr + col0 : nullptr;
+      if (col0 + 32 <= g.N && vec_y && (rrow == nullptr || vec_r)) {
+        // whole 32-column block inside N, vector accesses: straight-line
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + j);
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + j);
+          float4 o = make_float4(fmaf(v[j + 0], sc.x, sh.x), fmaf(v[j + 1], sc.y, sh.y), fmaf(v[j + 2], sc.z, sh.z),
+                                 fmaf(v[j + 3], sc.w, sh.w));
+          if (g.relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+          if (rrow) {
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + j));
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+          }
+          *reinterpret_cast<float4*>(yrow + j) = o;
+        }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float o[4];
-#pragma unroll
         const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + j);
         const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + j);
         o[0] = fmaf(v[j + 0], sc.x, sh.x);
@@ -165,27 +201,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
           for (int u = 0; u < 4; ++u) o[u] = fmaxf(o[u], 0.f);
         }
-        if (col0 + j + 3 < g.N) {
-          if (rrow) {
-            if (vec_r) {
-              const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + j));
-              o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-            } else {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) o[u] += __ldg(rrow + j + u);
-            }
-          }
-          if (vec_y) {
-            *reinterpret_cast<float4*>(yrow + j) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) yrow[j + u] = o[u];
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (col0 + j + u < g.N) yrow[j + u] = o[u] + (rrow ? __ldg(rrow + j + u) : 0.f);
-        }
+        for (int u = 0; u < 4; ++u)
+          if (col0 + j + u < g.N) yrow[j + u] = o[u] + (rrow ? __ldg(rrow + j + u) : 0.f);
       }
     }
   } else if (warp == 8) {
