@@ -337,10 +337,20 @@ int ptt_tc_gemm_launch(const PttGemmArgs& a, const void* wimg, cudaStream_t st) 
   p.wimg = static_cast<const __half*>(wimg);
   p.n_wblocks = ceil_div(a.N, 64);
   p.k_blocks = ceil_div(a.K, 64);
-  // widest tile that still gives the grid at least one CTA per SM (small problems are latency-, not throughput-bound)
+  // Tile width by a small cost model: these problems are a few waves of short pipelines, so what matters is the number
+  // of waves times (fixed per-CTA latency + k-blocks x the slower of producer and MMA issue per k-block), in cycles.
   const long long row_tiles = ceil_div(a.R, TBM);
-  int bn = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
-  while (bn > 64 && row_tiles * ceil_div(a.N, bn) * (a.batch > 0 ? a.batch : 1) < 148) bn >>= 1;
+  const int batch = a.batch > 0 ? a.batch : 1;
+  const int bn_max = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
+  int bn = bn_max;
+  long long best = -1;
+  for (int cand = bn_max; cand >= 64; cand >>= 1) {
+    const long long ctas = row_tiles * ceil_div(a.N, cand) * batch;
+    const long long waves = (ctas + 147) / 148;
+    const long long per_kb = 12LL * (cand / 2 > 70 ? cand / 2 : 70);
+    const long long t = waves * (6000 + (long long)p.k_blocks * (per_kb > 800 ? per_kb : 800));
+    if (best < 0 || t < best) { best = t; bn = cand; }
+  }
   if (bn == 64) return tc_launch<64>(p, st);
   if (bn == 128) return tc_launch<128>(p, st);
   return tc_launch<256>(p, st);
