@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     // top of the next tile: any arithmetic on them here would make the warp wait for the loads it has just issued.
     struct RowRaw { float px, py, pz, cx, cy, cz; int src; };
     const int plog2ns = 31 - __clz(ns);
+    const float inv_radius = 1.f / a.radius;
     auto row_raw = [&](int tile, int i) -> RowRaw {
       RowRaw w = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, -1};
       if (i >= 0) {
@@ -293,7 +294,12 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       if (w.src < 0) return make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
       if (a.pair_scalar != nullptr) return make_float4(w.px, 0.f, 0.f, __int_as_float(w.src));
       float dx = __fsub_rn(w.px, w.cx), dy = __fsub_rn(w.py, w.cy), dz = __fsub_rn(w.pz, w.cz);
-      if (a.normalize) { dx = __fdiv_rn(dx, a.radius); dy = __fdiv_rn(dy, a.radius); dz = __fdiv_rn(dz, a.radius); }
+      if (a.normalize) {
+        // x / radius as a branch-free reciprocal + one Newton correction (correctly rounded for normal operands): the IEEE
+        // division's slow-path branches cost ~1.4 k cycles per tile here (3 divisions, ~4 warps per scheduler)
+        auto div_r = [&](float x) { const float q = x * inv_radius; return fmaf(fmaf(-q, a.radius, x), inv_radius, q); };
+        dx = div_r(dx); dy = div_r(dy); dz = div_r(dz);
+      }
       return make_float4(dx, dy, dz, __int_as_float(w.src));
     };
     // layer-1 xyz weights of this thread's channels: kept in registers for up to two k-blocks, re-read (L1) beyond
@@ -318,9 +324,14 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     int sa = 0;                 // H1 ring slot
     uint32_t pa = 0;            // its phase
     for (int tile = blockIdx.x; tile < num_tiles; tile += stride, ++it) {
+      const bool prec0 = a.dbg != nullptr && blockIdx.x == 0 && pt == 0 && it < 30;
+      if (prec0) a.dbg[3000 + it * 4 + 0] = clock64();
       producer_bar();                                   // everyone is done reading s_info of the previous tile
+      if (prec0) a.dbg[3000 + it * 4 + 1] = clock64();
       if (pt < SF_TM) s_info[pt] = row_info(raw_cur);
+      if (prec0) a.dbg[3000 + it * 4 + 3] = clock64();
       producer_bar();
+      if (prec0) a.dbg[3000 + it * 4 + 2] = clock64();
       // issue the loads for the next two tiles now; they are consumed at the top of the next tile
       const RowRaw raw_nxt = row_raw(tile + stride, idx_next);
       const int idx_nn = row_index(tile + 2 * stride);

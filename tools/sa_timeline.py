@@ -17,7 +17,7 @@ xyz = torch.from_numpy(synth.make_clouds(B, N, 5, "dense")).cuda()
 feats = torch.randn(B, N, C, device="cuda") if C else None
 inds, new_xyz = ops.furthest_point_sampling(xyz, M, return_new_xyz=True)
 idx = ops.ball_query(new_xyz, xyz, r, 32)
-dbg = torch.zeros(4000, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(5000, dtype=torch.int64, device="cuda")
 for rep in range(3):
     dbg.zero_()
     L.ptt_debug_sa_timeline(dbg.data_ptr())
@@ -44,3 +44,6 @@ for it in range(6):
 print("producer (start wait ha_free, got it, H1 written):")
 for it in range(6):
     print("  tile", it, [int(d[2000 + it * 3 + j]) - t0 for j in range(3)])
+print("producer loop top (enter, after bar 1, after s_info written, after bar 2):")
+for it in range(6):
+    print("  tile", it, [int(d[3000 + it * 4 + j]) - t0 for j in (0, 1, 3, 2)])
