@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
     auto row_index = [&](int tile) -> int {          // ball-query result of this thread's row, -1 beyond the end
       const long long R = (long long)tile * SF_TM + pt;
       if (!(pt < SF_TM && tile < num_tiles && R < a.rows)) return -1;
-      return a.idx ? __ldg(a.idx + R) : (int)(R % ns);
+      return a.idx ? __ldg(a.idx + R) : (int)(R & (ns - 1));     // ns is a power of two
     };
     // The loads of a row's point and centre are issued one tile ahead and their values stay RAW in registers until the
     // top of the next tile: any arithmetic on them here would make the warp wait for the loads it has just issued.
