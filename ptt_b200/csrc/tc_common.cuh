@@ -267,6 +267,14 @@ __device__ __forceinline__ void ld_global_nc_v8(const float* p, float (&o)[8]) {
                : "l"(p));
 }
 
+// 1 / x for x in a normal range (softmax denominators, 1 <= x <= k): MUFU.RCP plus one Newton step -- full fp32 accuracy
+// without the IEEE division's slow-path branches (a branch costs ~30 cycles with 4-5 warps per scheduler)
+__device__ __forceinline__ float rcp_nr(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(fmaf(-x, r, 1.f), r, r);
+}
+
 // 2^x, one MUFU.EX2 (flush-to-zero: no denormal range fix-up around it)
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
