@@ -51,3 +51,37 @@ def test_reference_resolves_ext_and_registries_to_ptt_b200():
     r = subprocess.run([sys.executable, "-c", SCRIPT, REPO], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().startswith("OK 175")          # 175 state_dict keys
+
+
+REGISTRY_SCRIPT = r'''
+import os, sys
+repo = sys.argv[1]
+sys.path[:0] = [repo, os.path.join(repo, "oracle", "shims"), "/root/reference"]
+import torch
+torch.Tensor.cuda = lambda self, *a, **k: self
+torch.nn.Module.cuda = lambda self, *a, **k: self
+import ptt_b200.modules as m
+from ptt.models import transformer_block
+from easydict import EasyDict
+ref = dict(transformer_block.__all__)                 # the reference's own classes, before registration
+assert set(ref) == set(m.REGISTRY), set(ref) ^ set(m.REGISTRY)      # every registered name has a B200 twin
+m.register()
+n = 0
+for name in sorted(ref):
+    cfg = EasyDict(NAME=name, DIM_INPUT=32, DIM_MODEL=64, KNN=8, N_HEADS=4, N_LAYERS=2)
+    ours = transformer_block.build_transformer(cfg)   # the reference's factory (transformer_block/__init__.py:20-27)
+    assert type(ours) is m.REGISTRY[name], name
+    theirs = ref[name](d_points=32, d_model=64, k=8, heads=4, layers=2)
+    a = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in theirs.state_dict().items()}
+    assert a == b, (name, set(a) ^ set(b))            # checkpoints load by key and shape (tracker3d_template.py:110-118)
+    n += 1
+print("OK", n)
+'''
+
+
+@pytest.mark.reference
+def test_every_registered_transformer_block_has_a_state_dict_compatible_twin():
+    r = subprocess.run([sys.executable, "-c", REGISTRY_SCRIPT, REPO], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip() == "OK 9"

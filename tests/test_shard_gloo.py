@@ -65,3 +65,16 @@ def test_two_ranks_shard_and_reduce_times():
     assert res[0][2] == (5, 4, 3) and res[1][2] == (5, 4, 3)
     assert all(r[3] == 2.0 for r in res)                # max over ranks of (1 ms, 2 ms)
     assert all(abs(r[4] - 48 * 2 / 2e-3) < 1e-6 for r in res)
+
+
+def test_hot_path_net_has_exactly_the_hot_path_parameters():
+    """ptt_b200.train.HotPathNet (the trainable twin used by tools/train_step.py under DDP) exposes the reference's
+    parameter names for the hot path: its state_dict keys and shapes are those of synth.hot_path_layout(), which is what
+    HotPath consumes and what a reference checkpoint provides.  Construction only: no CUDA needed."""
+    from ptt_b200 import synth, train
+
+    net = train.HotPathNet()
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    want = {k: tuple(v) for k, v in synth.hot_path_layout().items()}
+    assert got == want
+    assert sum(p.numel() for p in net.parameters()) == 4106944
