@@ -314,36 +314,67 @@ extern "C" int ptt_sa_mlp_fwd(const float* xyz, const float* feats, int ldf, con
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 
-// one warp per (b, s): sim[b, s, t] = (S_s / max(|S_s|, eps)) . (T_t / max(|T_t|, eps)) for all t
-__global__ void __launch_bounds__(256) cosine_sim_kernel(const float* __restrict__ S, int lds, const float* __restrict__ T,
-                                                          int ldt, int n1, int n2, int f, long long rows,
-                                                          float* __restrict__ sim) {
+// inv[r] = 1 / max(|row r|, eps): one warp per feature row (F.cosine_similarity's eps = 1e-8)
+__global__ void __launch_bounds__(256) row_inv_norm_kernel(const float* __restrict__ X, int ld, int f, long long rows,
+                                                            float* __restrict__ inv) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  const float eps = 1e-8f;
-  for (long long row = warp; row < rows; row += nwarps) {      // row = b * n2 + s
-    const long long b = row / n2;
-    const float* srow = S + row * lds;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float* x = X + r * ld;
     float ss = 0.f;
-    for (int c = lane; c < f; c += 32) { const float v = __ldg(srow + c); ss = fmaf(v, v, ss); }
+    for (int c = lane; c < f; c += 32) { const float v = __ldg(x + c); ss = fmaf(v, v, ss); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float inv_s = 1.f / fmaxf(sqrtf(ss), eps);
-    for (int t = 0; t < n1; ++t) {
-      const float* trow = T + (b * n1 + t) * ldt;
-      float dot = 0.f, tt = 0.f;
-      for (int c = lane; c < f; c += 32) {
-        const float v = __ldg(trow + c);
-        dot = fmaf(v, __ldg(srow + c), dot);
-        tt = fmaf(v, v, tt);
-      }
+    if (lane == 0) inv[r] = 1.f / fmaxf(sqrtf(ss), 1e-8f);
+  }
+}
+
+// sim[b, s, t] = (S[b, s, :] . T[b, t, :]) * inv_s[b, s] * inv_t[b, t]: a 32 (search) x 64 (template) output tile per CTA,
+// 16-deep feature slabs staged in shared memory, 2 x 4 outputs per thread (exact fp32, CUDA cores: 2 MFLOP per frame)
+constexpr int CS_TS = 32, CS_TT = 64, CS_K = 16;
+__global__ void __launch_bounds__(256) cosine_sim_kernel(const float* __restrict__ S, int lds, const float* __restrict__ T,
+                                                          int ldt, const float* __restrict__ inv_s,
+                                                          const float* __restrict__ inv_t, int n1, int n2, int f,
+                                                          float* __restrict__ sim) {
+  __shared__ float As[CS_K][CS_TS + 1];
+  __shared__ float Bs[CS_K][CS_TT + 1];
+  const int b = blockIdx.z, s0 = blockIdx.x * CS_TS, t0 = blockIdx.y * CS_TT;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // thread -> rows ty*2.., columns tx*4..
+  const float* Sb = S + (size_t)b * n2 * lds;
+  const float* Tb = T + (size_t)b * n1 * ldt;
+  float acc[2][4] = {};
+  for (int k0 = 0; k0 < f; k0 += CS_K) {
+    for (int e = tid; e < CS_TS * CS_K; e += 256) {
+      const int r = e / CS_K, k = e % CS_K;
+      As[k][r] = (s0 + r < n2 && k0 + k < f) ? __ldg(Sb + (size_t)(s0 + r) * lds + k0 + k) : 0.f;
+    }
+    for (int e = tid; e < CS_TT * CS_K; e += 256) {
+      const int r = e / CS_K, k = e % CS_K;
+      Bs[k][r] = (t0 + r < n1 && k0 + k < f) ? __ldg(Tb + (size_t)(t0 + r) * ldt + k0 + k) : 0.f;
+    }
+    __syncthreads();
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        tt += __shfl_xor_sync(0xffffffffu, tt, o);
+    for (int k = 0; k < CS_K; ++k) {
+      const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float bv = Bs[k][tx * 4 + j];
+        acc[0][j] = fmaf(a0, bv, acc[0][j]);
+        acc[1][j] = fmaf(a1, bv, acc[1][j]);
       }
-      if (lane == 0) sim[row * n1 + t] = (dot * inv_s) * (1.f / fmaxf(sqrtf(tt), eps));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int sr = s0 + ty * 2 + i;
+    if (sr >= n2) continue;
+    const float is = __ldg(inv_s + (size_t)b * n2 + sr);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tc = t0 + tx * 4 + j;
+      if (tc < n1) sim[((size_t)b * n2 + sr) * n1 + tc] = (acc[i][j] * is) * __ldg(inv_t + (size_t)b * n1 + tc);
     }
   }
 }
@@ -364,13 +395,15 @@ __global__ void __launch_bounds__(256) cosine_rows_kernel(const float* __restric
 
 struct CosWorkspace {
   int ldx;
-  size_t sim, x, sa, total;   // float offsets
+  size_t sim, x, inv_s, inv_t, sa, total;   // float offsets
 };
 bool cos_workspace(int B, int n1, int n2, int f, int n_layers, const int* h_dims, CosWorkspace* W) {
   W->ldx = round_up(3 + f, 4);
   size_t off = 0;
   W->sim = off; off += align_up((size_t)B * n2 * n1, 64);
   W->x = off;   off += align_up((size_t)B * n1 * W->ldx, 64);
+  W->inv_s = off; off += align_up((size_t)B * n2, 64);
+  W->inv_t = off; off += align_up((size_t)B * n1, 64);
   W->sa = off;
   const size_t sa_bytes = ptt_sa_mlp_workspace_bytes(B, n1, n2, n1, 3 + f, n_layers, h_dims);
   if (sa_bytes == 0) return false;
@@ -403,10 +436,13 @@ extern "C" int ptt_cosine_fusion_fwd(const float* search_feats, int lds, const f
   float* sim = ws + W.sim;
   float* X = ws + W.x;
   {
-    const long long rows = (long long)B * n2;
-    cosine_sim_kernel<<<(unsigned)llmin_((rows + 7) / 8, 148LL * 8), 256, 0, st>>>(search_feats, lds, template_feats, ldt, n1, n2,
-                                                                                   f, rows, sim); PTT_LAUNCHED();
-    const long long trows = (long long)B * n1;
+    const long long rows = (long long)B * n2, trows = (long long)B * n1;
+    float* inv_s = ws + W.inv_s;
+    float* inv_t = ws + W.inv_t;
+    row_inv_norm_kernel<<<(unsigned)llmin_((rows + 7) / 8, 148LL * 8), 256, 0, st>>>(search_feats, lds, f, rows, inv_s); PTT_LAUNCHED();
+    row_inv_norm_kernel<<<(unsigned)llmin_((trows + 7) / 8, 148LL * 8), 256, 0, st>>>(template_feats, ldt, f, trows, inv_t); PTT_LAUNCHED();
+    cosine_sim_kernel<<<dim3(ceil_div(n2, CS_TS), ceil_div(n1, CS_TT), B), 256, 0, st>>>(search_feats, lds, template_feats, ldt,
+                                                                                         inv_s, inv_t, n1, n2, f, sim); PTT_LAUNCHED();
     cosine_rows_kernel<<<(unsigned)llmin_((trows * W.ldx + 255) / 256, 148LL * 8), 256, 0, st>>>(template_xyz, template_feats,
                                                                                                  ldt, f, trows, X, W.ldx); PTT_LAUNCHED();
   }
