@@ -197,10 +197,12 @@ def test_hot_path_full_batch_properties():
 
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, -2])
-@pytest.mark.parametrize("shape", [(3, 128, 256, 512, 16), (5, 64, 64, 128, 8), (2, 100, 32, 256, 4), (1, 32, 128, 64, 32)])
+@pytest.mark.parametrize("shape", [(3, 128, 256, 512, 16), (5, 64, 64, 128, 8), (2, 100, 32, 256, 4), (1, 32, 128, 64, 32),
+                                   (1, 33, 32, 128, 4), (1, 35, 64, 512, 2), (3, 21, 16, 256, 1)])
 def test_transformer_cluster_sizes_agree_with_port(cluster, shape):
     """Every thread-block-cluster size of the tcgen05 transformer passes (weights multicast to 1, 2 or 4 CTAs),
-    including tile counts that are not a multiple of the cluster size (dummy tiles), against the CPU port."""
+    including tile counts that are not a multiple of the cluster size (dummy tiles) and pair counts that are not a
+    multiple of 32 (the guarded last block of the transposed epilogues), against the CPU port."""
     import ctypes
     from ptt_b200 import _lib
     B, n, dp, dm, k = shape
