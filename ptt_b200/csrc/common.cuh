@@ -28,6 +28,15 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 static inline long long llmin_(long long a, long long b) { return a < b ? a : b; }
 
+// Function attributes (opt-in shared memory, cluster occupancy) belong to a device context: launch helpers keep their
+// "configured" state per device so that one process may drive several GPUs.
+constexpr int PTT_MAX_DEVICES = 64;
+static inline int ptt_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PTT_MAX_DEVICES) dev = 0;
+  return dev;
+}
+
 // a*a + b*b + c*c exactly as nvcc's default contraction emits it for upstream pointnet2_ops
 // (oracle/probe_contraction.sh): FMUL on the middle term, then two FFMAs.  Written with intrinsics
 // so the result does not depend on how the compiler feels about this translation unit.

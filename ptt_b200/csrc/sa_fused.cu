@@ -538,16 +538,16 @@ template <int D1, int D2, int D3>
 int sf_launch(const SaFusedArgs& a, cudaStream_t st) {
   using Cfg = SfCfg<D1, D2, D3>;
   auto kern = sa_fused_kernel<D1, D2, D3>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[PTT_MAX_DEVICES] = {};
+  const int dev = ptt_current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    configured[dev] = true;
   }
   const long long tiles = (a.rows + SF_TM - 1) / SF_TM;
   int sms = 148;
-  int dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)llmin_(tiles, sms);
   kern<<<grid, SF_THREADS, Cfg::SMEM_BYTES, st>>>(a, (int)tiles); PTT_LAUNCHED();
   return ptt_launch_status();

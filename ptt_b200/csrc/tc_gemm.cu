@@ -299,11 +299,12 @@ template <int BN>
 int tc_launch(const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   auto kern = tc_gemm_kernel<BN>;
-  static bool configured = false;   // attribute is per function, idempotent; racing threads set the same value
-  if (!configured) {
+  static bool configured[PTT_MAX_DEVICES] = {};   // per device; idempotent, racing threads set the same value
+  const int dev = ptt_current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    configured[dev] = true;
   }
   dim3 grid(ceil_div(p.g.R, TBM), ceil_div(p.g.N, BN), p.g.batch > 0 ? p.g.batch : 1);
   kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p); PTT_LAUNCHED();
