@@ -78,3 +78,22 @@ def test_hot_path_net_has_exactly_the_hot_path_parameters():
     want = {k: tuple(v) for k, v in synth.hot_path_layout().items()}
     assert got == want
     assert sum(p.numel() for p in net.parameters()) == 4106944
+
+
+def test_bench_algorithmic_work_matches_the_survey_figures():
+    """bench.py's per-frame algorithmic FLOPs (the numerator of roofline.achieved) are SURVEY.md 8(d)'s: SA MLPs 3.65 GFLOP +
+    transformer blocks 5.24 GFLOP = 8.89 GFLOP per frame at ptt.yaml sizes."""
+    import argparse
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    a = argparse.Namespace(nsearch=1024, ntemplate=512, batch=48)
+    f = bench.algorithmic(a)
+    sa = sum(v for k, v in f.items() if k.endswith(".mlp"))
+    tr = sum(v for k, v in f.items() if k.endswith(".transformer"))
+    assert abs(sa / 1e9 - 3.65) < 0.01 and abs(tr / 1e9 - 5.24) < 0.01 and abs((sa + tr) / 1e9 - 8.89) < 0.01
+    assert set(bench.algorithmic_bytes(a)) == {"%s.sa%d.ball_query" % (t, l) for t in ("search", "template") for l in (1, 2, 3)} | {
+        "search.sa1.fps", "template.sa1.fps", "box.sa.fps", "box.sa.ball_query"}
