@@ -252,6 +252,10 @@ class HotPath:
                 m = b_xyz.shape[1]
                 est = self.refine(box.reshape(B * m, box.shape[2])).reshape(B, m, -1)           # :88
                 est[:, :, :3] += b_xyz                                                           # :90-91
+                # the proposal the evaluation loop keeps (eval_tracking_utils.py:268-270: argmax of the score column):
+                # selected here so that a tracking loop only has to read back 5 floats per frame
+                best_idx = est[:, :, 4].argmax(dim=1)
+                best_box = est[torch.arange(B, device=est.device), best_idx]
             cos_cm = ops.pm_to_cm(cos_pm)
             vf_cm = ops.pm_to_cm(vf[:, :, :d + 1].contiguous())
         cur.wait_stream(s1)
@@ -260,7 +264,7 @@ class HotPath:
                "template_seeds": t_xyz, "template_feats": t_feat, "template_inds": t_inds,
                "cosine_feats": cos_cm, "centroid_feats": cen, "pred_centroids_cls": cls, "pred_centroids_votes": votes,
                "votes_feats": vf_cm, "pred_box_center": b_xyz, "box_sa_feats": b_feat_pm, "box_feats": box,
-               "pred_box_data": est}
+               "pred_box_data": est, "best_box": best_box, "best_idx": best_idx}
         if not torch.cuda.is_current_stream_capturing():
             for t in list(out.values()) + [t_feat_pm, s_feat_pm, cos_pm, vin, res, vf]:
                 t.record_stream(cur)

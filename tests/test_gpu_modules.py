@@ -334,6 +334,11 @@ def test_full_model_vs_reference_fixture(golden):
     want = torch_port.full_model_frame(sd, t(gd["full/search"]), t(gd["full/template"]))
     same = _check_full(out, want, sd)
     assert same, "box-centre FPS picks differ from the reference run"
+    # the proposal selection of the evaluation loop (eval_tracking_utils.py:268-270) done on the device
+    est = out["pred_box_data"].cpu().numpy()
+    pick = est[:, :, 4].argmax(1)
+    assert np.array_equal(out["best_idx"].cpu().numpy(), pick)
+    assert np.array_equal(out["best_box"].cpu().numpy(), est[np.arange(est.shape[0]), pick])
     np.testing.assert_allclose(out["pred_box_center"].cpu().numpy(), gd["full/pred_box_center"], rtol=1e-5, atol=1e-4)
     np.testing.assert_allclose(out["pred_box_data"].cpu().numpy(), gd["full/pred_box_data"], **FP_TOL)
 
