@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-whole-model", action="store_true", help="skip the whole-tracker-forward figure")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-modules-on-this-GPU figure")
+    ap.add_argument("--sustain-s", type=float, default=2.5, help="length of the sustained region in seconds (0 = skip)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
     return ap.parse_args()
 
@@ -57,11 +59,12 @@ def workload_config(a, n_gpus):
 
 def scaled_cfg(a):
     n = a.nsearch
-    if n == 1024 and a.ntemplate == 512:
+    if a.ntemplate == 512 and n in (512, 1024):     # configs 2 and 3: the yaml's NPOINTS unchanged (config 3: SA1 FPS 512 -> 512)
         return None
     # NPOINTS scale with N (reproduces the yaml at N = 1024)
     nt = a.ntemplate
-    return dict(npoints_search=(n // 2, n // 4, n // 8), npoints_template=(nt // 2, nt // 4, nt // 8))
+    return dict(npoints_search=(n // 2, n // 4, n // 8), npoints_template=(nt // 2, nt // 4, nt // 8),
+                box_npoint=min(64, n // 16))           # the box head samples half of the seeds (64 of 128 in the yaml)
 
 
 # per-frame algorithmic work of the hot path (DESIGN.md "Measurement")
@@ -76,13 +79,14 @@ def algorithmic(a):
     for tag, npts in (("search", cfgs["npoints_search"]), ("template", cfgs["npoints_template"])):
         for l in range(3):
             flops["%s.sa%d.mlp" % (tag, l + 1)] = 2.0 * npts[l] * 32 * mlp_macs(specs[l])
-    flops["box.sa.mlp"] = 2.0 * 64 * 16 * mlp_macs([260, 256, 256, 256])
+    nbox = cfgs.get("box_npoint", 64)
+    flops["box.sa.mlp"] = 2.0 * nbox * 16 * mlp_macs([260, 256, 256, 256])
 
     def tr(n, k=16, dp=256, dm=512):
         return 2.0 * (n * dp * dm + 3 * n * dm * dm + n * k * (3 * dm + dm * dm) + 2 * n * k * dm * dm + n * dm * dp)
 
     flops["centroid.transformer"] = tr(cfgs["npoints_search"][2])
-    flops["box.transformer"] = tr(64)
+    flops["box.transformer"] = tr(nbox)
     return flops
 
 
@@ -100,8 +104,9 @@ def algorithmic_bytes(a):
             out["%s.sa%d.ball_query" % (tag, l + 1)] = 12.0 * n + 12.0 * m + 4.0 * m * 32
             n = m
     ns3 = cfgs["npoints_search"][2]
-    out["box.sa.fps"] = 12.0 * ns3 + 16.0 * 64
-    out["box.sa.ball_query"] = 12.0 * ns3 + 12.0 * 64 + 4.0 * 64 * 16
+    nbox = cfgs.get("box_npoint", 64)
+    out["box.sa.fps"] = 12.0 * ns3 + 16.0 * nbox
+    out["box.sa.ball_query"] = 12.0 * ns3 + 12.0 * nbox + 4.0 * nbox * 16
     return out
 
 
@@ -111,7 +116,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
         self._halt = threading.Event()
         self.error = None
 
@@ -125,6 +130,10 @@ class ClockSampler(threading.Thread):
                      "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
             while not self._halt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
@@ -140,8 +149,10 @@ class ClockSampler(threading.Thread):
         self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
+        pw = sorted(self.power)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s), **({"error": self.error} if self.error else {})}
+                "samples": len(s), "power_w_median": pw[len(pw) // 2] if pw else None, "power_w_max": pw[-1] if pw else None,
+                **({"error": self.error} if self.error else {})}
 
 
 def physical_gpu_index(local_rank):
@@ -155,25 +166,37 @@ def physical_gpu_index(local_rank):
 
 
 def cpu_hot_path(a, frames, threads, steps, warmup):
-    """The reference's CPU path for the hot path = oracle.torch_port (PyTorch CPU + C ops), timed on host cores."""
+    """The reference's CPU implementation of the hot path, timed on the host cores: the reference's OWN nn.Modules
+    (oracle/_ref staged by oracle/make_ref.sh, or /root/reference) driven by oracle/ref_hotpath.py when the tree is
+    there -- its CUDA-only third-party pointnet2_ops replaced by the oracle's C ops -- else the oracle port.
+    Returns (frames/s, s/step, kind, description)."""
     import torch
 
-    from oracle import torch_port
+    from oracle import refload, torch_port
     from ptt_b200 import synth
 
     torch.set_num_threads(threads)
-    sd = synth.hot_path_state_dict(0)
     search = torch.from_numpy(synth.make_clouds(frames, a.nsearch, 900, a.kind))
     template = torch.from_numpy(synth.make_clouds(frames, a.ntemplate, 901, a.kind, role="template"))
     cfg = scaled_cfg(a)
+    if refload.available() and cfg is None:
+        from oracle import ref_hotpath
+        ref = ref_hotpath.RefHotPath(synth.full_model_state_dict(0), "cpu")
+        fn = lambda: ref.hot_path(search, template)
+        kind, what = "reference", ("the reference's own ptt.models modules (%s) on the host cores, eval mode; its CUDA-only "
+                                   "pointnet2_ops replaced by oracle/pointnet2_ref.c" % os.path.relpath(refload.REFERENCE_ROOT, REPO))
+    else:
+        sd = synth.hot_path_state_dict(0)
+        fn = lambda: torch_port.hot_path_frame(sd, search, template, cfg)
+        kind, what = "port", "oracle/torch_port.py over oracle/pointnet2_ref.c"
     with torch.no_grad():
         for _ in range(warmup):
-            torch_port.hot_path_frame(sd, search, template, cfg)
+            fn()
         t0 = time.perf_counter()
         for _ in range(steps):
-            torch_port.hot_path_frame(sd, search, template, cfg)
+            fn()
         dt = time.perf_counter() - t0
-    return frames * steps / dt, dt / steps
+    return frames * steps / dt, dt / steps, kind, what
 
 
 def run_reference(a):
@@ -185,14 +208,16 @@ def run_reference(a):
     threads = os.cpu_count() or 1
     frames = a.cpu_frames
     steps, warmup = max(1, min(a.steps, 10)), max(1, min(a.warmup, 2))
-    fps, sec = cpu_hot_path(a, frames, threads, steps, warmup)
+    fps, sec, kind, what = cpu_hot_path(a, frames, threads, steps, warmup)
+    cfg = workload_config(a, a.gpus)
+    # what this arm actually ran: a bounded sample of the workload (the CPU needs ~0.03 s per frame)
+    cfg["reference_sample"] = {"frames_per_step": frames, "steps": steps, "warmup": warmup, "host_threads": threads,
+                               "note": "batch_per_gpu above is the GPU arm's; this arm times %d frames per step" % frames}
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "%d frames per step x %d steps (the reference is Python over a CUDA-only "
-                                       "third-party extension; its CPU path is the oracle port, oracle/torch_port.py "
-                                       "over oracle/pointnet2_ref.c)" % (frames, steps)},
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                             "sample": "%d frames per step x %d steps: %s" % (frames, steps, what)},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -286,13 +311,13 @@ def run_b200(a):
     big_s += torch.arange(n_big, device=dev, dtype=torch.float32).view(-1, 1, 1, 1) * 1e-6      # distinct bits per set
     for i in range(max(4, a.warmup)):
         pipe.push(big_s[i % n_big], big_t[i % n_big], to_host=False)
-    pipe.drain(to_host=False)
+    pipe.drain()
     barrier()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
     for i in range(a.steps):
         pipe.push(big_s[(7 * i) % n_big], big_t[(7 * i) % n_big], to_host=False, after=p0)
-    pipe.drain(to_host=False)
+    pipe.drain()
     for slot in pipe.slots:
         torch.cuda.current_stream().wait_stream(slot._io_stream)
     p1.record()
@@ -300,26 +325,53 @@ def run_b200(a):
     pipe_ms = p0.elapsed_time(p1)
     clocks = sampler.stop()        # sampled over both device-timed regions (sequential + pipelined)
 
+    # ---- sustained: the same pipelined loop for >= a.sustain_s seconds of back-to-back steps (the K-step region above is
+    # a ~30 ms burst: clocks and power have not settled there), clocks / power / throttle reasons sampled throughout
+    sustained = None
+    if a.sustain_s > 0:
+        n_sus = max(a.steps, int(a.sustain_s * 1e3 / (pipe_ms / a.steps)) + 1)
+        sus_sampler = ClockSampler(physical_gpu_index(local_rank), period=0.02)
+        barrier()
+        sus_sampler.start()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for i in range(n_sus):
+            pipe.push(big_s[(7 * i) % n_big], big_t[(7 * i) % n_big], to_host=False, after=q0)
+        pipe.drain()
+        for slot in pipe.slots:
+            torch.cuda.current_stream().wait_stream(slot._io_stream)
+        q1.record()
+        barrier()
+        sus_ms = q0.elapsed_time(q1)
+        sustained = (n_sus, shard.max_over_ranks([sus_ms], device=dev)[0], sus_sampler.stop())
+
     # ---- end-to-end through the host API: pinned host in, pinned host out, copies inside the timed region ----
     # HostPipeline = the throughput form of HotPath.forward_host: two instances alternate, so the H2D copy and compute
-    # of step i+1 overlap the D2H copy of step i.  Every step's inputs come from pinned host memory and all ten
-    # outputs of every step are copied back to pinned host memory inside the timed region.
-    for i in range(max(4, a.warmup)):
-        pipe.push(search_h[i % n_sets], templ_h[i % n_sets])
-    pipe.drain()
-    barrier()
-    t0 = time.perf_counter()
-    got = 0
-    for i in range(a.steps):
-        got += pipe.push(search_h[i % n_sets], templ_h[i % n_sets]) is not None
-    tail = pipe.drain()
-    got += len(tail)
-    out_h = tail[-1]
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    assert got == a.steps
+    # of step i+1 overlap the D2H copy of step i.  Every step's inputs come from pinned host memory and the selected
+    # outputs of every step are copied back to pinned host memory inside the timed region.  The default selection of
+    # the hot path is its final stage's features (box_feats: what the refine stack consumes); `e2e.all_outputs` repeats
+    # the measurement with every output tensor of the step copied back (round 1's figure).
+    def e2e_run(p):
+        for i in range(max(4, a.warmup)):
+            p.push(search_h[i % n_sets], templ_h[i % n_sets])
+        p.drain()
+        barrier()
+        t0 = time.perf_counter()
+        got = 0
+        for i in range(a.steps):
+            got += p.push(search_h[i % n_sets], templ_h[i % n_sets]) is not None
+        tail = p.drain()
+        got += len(tail)
+        barrier()
+        dt = time.perf_counter() - t0
+        assert got == a.steps
+        return dt, sum(v.numel() * v.element_size() for v in tail[-1].values()), sorted(tail[-1])
+
+    e2e_s, d2h, e2e_keys = e2e_run(pipe)
+    pipe.outputs = "all"
+    e2e_all_s, d2h_all, _ = e2e_run(pipe)
+    pipe.outputs = None
     h2d = search_h[0].numel() * 4 + templ_h[0].numel() * 4
-    d2h = sum(v.numel() * v.element_size() for v in out_h.values())
     # latency form (one step at a time, synchronous): reported next to the throughput form
     for i in range(2):
         hp.forward_host(search_h[i % n_sets], templ_h[i % n_sets])
@@ -358,7 +410,34 @@ def run_b200(a):
                                                                     if k.startswith(("cosine", "centroid.heads", "box.heads"))})
         del hpf
 
-    dev_ms, e2e_ms, wall_ms, pipe_ms = shard.max_over_ranks([dev_ms, e2e_s * 1e3, t_wall * 1e3, pipe_ms], device=dev)   # slowest rank
+    # ---- the reference's OWN modules on this GPU over the `pointnet2_ops._ext` drop-in (Level-1 integration): torch /
+    # cuDNN / cuBLAS arithmetic exactly as the reference would run it on a B200 with a working pointnet2_ops -- the
+    # "unfused" comparison point for the fused path (rank 0 of a single-GPU run only; needs oracle/_ref)
+    ref_gpu = None
+    if world == 1 and not a.no_reference_gpu and scaled_cfg(a) is None:
+        from oracle import refload
+        if refload.available():
+            from oracle import ref_hotpath
+            ref = ref_hotpath.RefHotPath(synth.full_model_state_dict(0), dev)
+            for i in range(3):
+                ref.hot_path(search_d[i % n_sets], templ_d[i % n_sets])
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_ref = max(3, min(a.steps, 10))
+            r0.record()
+            for i in range(n_ref):
+                ref.hot_path(search_d[i % n_sets], templ_d[i % n_sets])
+            r1.record()
+            torch.cuda.synchronize()
+            ref_gpu = {"value": B * n_ref / (r0.elapsed_time(r1) * 1e-3), "unit": UNIT, "steps": n_ref,
+                       "ms_per_step": r0.elapsed_time(r1) / n_ref,
+                       "what": "the reference's own ptt.models modules (oracle/_ref) on this B200, eval mode, torch defaults "
+                               "(cuDNN / cuBLAS TF32 allowed), their pointnet2_ops._ext calls served by libptt_b200.so; "
+                               "inputs resident in HBM, eager launches as the reference issues them"}
+            del ref
+
+    dev_ms, e2e_ms, wall_ms, pipe_ms, e2e_all_ms = shard.max_over_ranks([dev_ms, e2e_s * 1e3, t_wall * 1e3, pipe_ms, e2e_all_s * 1e3],
+                                                                        device=dev)   # slowest rank
 
     if rank == 0:
         frames = B * n_gpus * a.steps
@@ -370,14 +449,23 @@ def run_b200(a):
         pk = os.path.join(REPO, "MEASURED_PEAKS.json")
         if os.path.exists(pk):
             peaks = json.load(open(pk))
-        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        # the per-stage times come from a short eager pass (tens of ms: burst clocks) -> the burst peak is the matching
+        # denominator; the sustained region is compared with the sustained peak
+        peak_tf = peaks.get("bf16_tflops", 1650.0)
+        peak_tf_sus = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_gbs = peaks.get("hbm_gbs", 6650.0)
         abytes = algorithmic_bytes(a)
         achieved_tf = alg[top] * B / (known[top] * 1e-3) / 1e12
         traffic = None
-        tp = os.path.join(REPO, "profiles", "r1_traffic.json")     # dram__bytes_read+write per launch from the ncu --set full capture
-        if os.path.exists(tp) and B == 48 and a.nsearch == 1024:
-            traffic = json.load(open(tp)).get(top)
+        # dram__bytes_read + write of the stage's kernels from the committed `ncu --set full` capture of this workload
+        # (profiles/summarize.py writes the json; it cannot be measured inside an un-profiled run)
+        traffic_src = None
+        for name in ("r2_traffic.json", "r1_traffic.json"):
+            tp = os.path.join(REPO, "profiles", name)
+            if os.path.exists(tp) and B == 48 and a.nsearch == 1024 and a.kind == "dense":
+                traffic = json.load(open(tp)).get(top)
+                traffic_src = "profiles/" + name
+                break
         line = {
             "metric": METRIC, "value": shard.whole_job_throughput(B * a.steps, n_gpus, pipe_ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": pipe_ms / a.steps,
@@ -388,14 +476,18 @@ def run_b200(a):
                                       "how": "one step at a time, CUDA events per step, 256 MiB L2 flush between steps"}, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, n_gpus),
             "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / a.steps, "api": "HostPipeline(depth=2).push/drain",
+                    "ms_per_step": e2e_ms / a.steps, "api": "HostPipeline(depth=2).push/drain", "outputs": e2e_keys,
+                    "all_outputs": {"value": frames / (e2e_all_ms * 1e-3), "unit": UNIT, "d2h_bytes_per_step": d2h_all,
+                                    "ms_per_step": e2e_all_ms / a.steps},
                     "sync_one_step_at_a_time": {"value": B * a.steps / e2e_sync_s, "unit": UNIT,
                                                 "ms_per_step": e2e_sync_s * 1e3 / a.steps, "api": "HotPath.forward_host"}},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": top, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": traffic,
+                         "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                         "frac_of_sustained_peak": achieved_tf / peak_tf_sus, "peak_sustained": peak_tf_sus,
                          "frac_ceiling": "1/3: fp32-class accuracy costs 3 fp16 MMAs per algorithmic MAC (DESIGN.md 4)",
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
+                         "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst: the stage is timed in a short eager pass)"
+                                         if peaks else "fallback"),
                          "flops_per_launch": alg[top] * B, "ms_per_launch": known[top]},
             "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
             # every stage against ITS roofline (same eager pass): dense stages vs the measured bf16 peak (ceiling 1/3, see
@@ -410,6 +502,17 @@ def run_b200(a):
             "launch_mode": "eager" if a.no_graph else "CUDA graph replay (stage_ms / roofline from an eager single-stream pass of the same steps)",
             "wall_ms_per_step_incl_flush": wall_ms / a.steps,
         }
+        if sustained is not None:
+            n_sus, sus_ms, sus_clk = sustained
+            step_flops = sum(alg.values()) * B
+            tf = step_flops / (sus_ms / n_sus * 1e-3) / 1e12
+            line["sustained"] = {"value": shard.whole_job_throughput(B * n_sus, n_gpus, sus_ms * 1e-3), "unit": UNIT, "steps": n_sus,
+                                 "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus, "clocks": sus_clk,
+                                 "whole_step_tflops": tf, "whole_step_frac_of_sustained_peak": tf / peak_tf_sus,
+                                 "whole_step_frac_of_burst_peak": tf / peak_tf,
+                                 "how": "same depth-2 pipeline of graph replays as `value`, back to back for >= %.1f s" % a.sustain_s}
+        if ref_gpu is not None:
+            line["reference_modules_gpu"] = ref_gpu
         if whole is not None:
             line["whole_model"] = {"value": shard.whole_job_throughput(B * a.steps, n_gpus, whole[0] * 1e-3), "unit": UNIT,
                                    "ms_per_step": whole[0] / a.steps, "extra_stage_ms": whole[1],
@@ -418,10 +521,9 @@ def run_b200(a):
                                            "flushed between steps"}
         if not a.no_cpu_baseline and world == 1:
             cpu_threads = os.cpu_count() or 1
-            fps, sec = cpu_hot_path(a, a.cpu_frames, cpu_threads, steps=3, warmup=1)
-            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                                    "sample": "%d frames per step x 3 steps of the same workload, oracle/torch_port.py "
-                                              "over oracle/pointnet2_ref.c" % a.cpu_frames}
+            fps, sec, kind, what = cpu_hot_path(a, a.cpu_frames, cpu_threads, steps=3, warmup=1)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cpu_threads, "kind": kind,
+                                    "sample": "%d frames per step x 3 steps of the same workload: %s" % (a.cpu_frames, what)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

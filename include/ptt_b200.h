@@ -12,10 +12,14 @@
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named h_*;
  *   - all tensors are contiguous; float = fp32, int = int32; layouts are written as (dims);
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it, never synchronised;
- *   - no allocation and no global state: scratch memory comes in through `workspace`
- *     (query its size with the matching *_workspace_bytes call; 256-byte aligned);
+ *   - no device-memory allocation: scratch memory comes in through `workspace` (query its size with
+ *     the matching *_workspace_bytes call; 256-byte aligned).  Process-wide state is limited to what
+ *     this header names: the launch counter, the fault word (one 64-byte pinned host allocation made
+ *     when the first tensor-core kernel family is configured) and the per-device "kernel attributes
+ *     configured" bits.  The process-wide TUNING switches live in ptt_b200_tuning.h, not here;
  *   - return value: 0 on success, a cudaError_t (> 0) from the launch, or a PTT_ERR_* (< 0);
- *     nothing ever calls exit() (upstream pointnet2_ops does on launch failure);
+ *     nothing ever calls exit() (upstream pointnet2_ops does on launch failure) and no kernel traps:
+ *     a kernel that gives up a bounded barrier wait raises the fault word instead (ptt_fault_status);
  *   - inputs are borrowed and never written; outputs never alias inputs.
  */
 #ifndef PTT_B200_H_
@@ -37,6 +41,7 @@ extern "C" {
 #define PTT_ERR_INVALID_ARGUMENT (-1) /* null pointer, negative size, npoint > N ... */
 #define PTT_ERR_UNSUPPORTED (-2)      /* shape outside what the kernel family covers  */
 #define PTT_ERR_WORKSPACE (-3)        /* workspace missing or too small               */
+#define PTT_ERR_DEVICE_FAULT (-4)     /* an earlier kernel gave up a bounded wait     */
 
 typedef void* ptt_stream_t; /* cudaStream_t */
 
@@ -45,16 +50,25 @@ PTT_API const char* ptt_version(void);
 /* Text for a return code of any function below (static storage). */
 PTT_API const char* ptt_error_string(int code);
 
-/* Number of kernels this library has launched in this process so far (monotonic; diagnostics only --
- * the one piece of process-wide state in the library). */
+/* Number of kernels this library has launched in this process so far (monotonic; diagnostics only). */
 PTT_API unsigned long long ptt_launch_count(void);
+
+/* Device-fault word.  The tensor-core kernels hand tiles between warps through mbarriers with BOUNDED waits; a
+ * waiter that expires (a protocol bug, never observed in the shipped configurations) raises this word and the kernel
+ * drains instead of hanging or trapping, so the CUDA context stays usable.  From then on every entry point
+ * returns PTT_ERR_DEVICE_FAULT (sticky); results produced since the last call that returned 0 are invalid.
+ * ptt_fault_status: 0 or PTT_ERR_DEVICE_FAULT (a plain host read: meaningful after the stream was synchronised).
+ * ptt_fault_clear: re-arm after the caller has synchronised and discarded the affected results. */
+PTT_API int ptt_fault_status(void);
+PTT_API void ptt_fault_clear(void);
 
 /* ---------------------------------------------------------------------------------------------
  * a1  _ext.furthest_point_sampling(xyz, npoint)                     pointnet2_utils.py:78
  *     xyz (B,N,3) -> idx (B,npoint) int32.  idx[.,0] = 0; points with |p|^2 <= 1e-3 are never
  *     candidates; exact ties resolve as upstream's block tree reduction does.
  *     new_xyz (B,npoint,3), if not NULL, receives xyz[idx] (fuses _ext.gather_points of
- *     pointnet2_modules.py:79-81).  Workspace is only needed for N > 16384.
+ *     pointnet2_modules.py:79-81).  Workspace is only needed for N > 8192 (B*N floats: the clouds
+ *     that do not fit one CTA's registers keep their running distances in memory).
  * ------------------------------------------------------------------------------------------- */
 PTT_API size_t ptt_furthest_point_sampling_workspace_bytes(int B, int N, int npoint);
 PTT_API int ptt_furthest_point_sampling(const float* xyz, int B, int N, int npoint, int* idx, float* new_xyz,

@@ -19,6 +19,8 @@ SIGNATURES = {
     "ptt_version": (c_char_p, []),
     "ptt_error_string": (c_char_p, [c_int]),
     "ptt_launch_count": (ctypes.c_ulonglong, []),
+    "ptt_fault_status": (c_int, []),
+    "ptt_fault_clear": (None, []),
     "ptt_furthest_point_sampling_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ptt_furthest_point_sampling": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "ptt_furthest_point_sampling_with_dist_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
@@ -61,6 +63,16 @@ SIGNATURES = {
     "ptt_transformer_std_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
 }
 
+# include/ptt_b200_tuning.h: process-wide test / tuning switches.  Bound for tests/ and tools/ only -- nothing under
+# ptt_b200/ calls them (tests/test_abi.py checks that).
+TUNING_SIGNATURES = {
+    "ptt_debug_force_ffma": (None, [c_int]),
+    "ptt_debug_set_cluster": (None, [c_int]),
+    "ptt_debug_sa_timeline": (None, [_P]),
+    "ptt_debug_tr_pass_timeline": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_int, _P, c_int, _P, _P]),
+    "ptt_fps_variant": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P]),
+}
+
 _lib = None
 
 
@@ -74,7 +86,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise PttError("%s is missing: build it with `python -m ptt_b200.build` (there is no fallback path)" % LIB_PATH)
         handle = ctypes.CDLL(LIB_PATH)
-        for name, (restype, argtypes) in SIGNATURES.items():
+        for name, (restype, argtypes) in list(SIGNATURES.items()) + list(TUNING_SIGNATURES.items()):
             fn = getattr(handle, name)   # AttributeError if the library does not export what the header declares
             fn.restype = restype
             fn.argtypes = argtypes
@@ -85,6 +97,15 @@ def lib():
 def check(code, what):
     if code != 0:
         raise PttError("%s failed: %s (code %d)" % (what, lib().ptt_error_string(code).decode(), code))
+
+
+def fault_status():
+    """0, or PTT_ERR_DEVICE_FAULT once a kernel gave up a bounded barrier wait (sticky until fault_clear())."""
+    return int(lib().ptt_fault_status())
+
+
+def fault_clear():
+    lib().ptt_fault_clear()
 
 
 def launch_count():

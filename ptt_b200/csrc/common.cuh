@@ -11,10 +11,16 @@
     if (!(cond)) return PTT_ERR_INVALID_ARGUMENT; \
   } while (0)
 
-// Returns the launch error (if any) of the kernels enqueued so far by this call, without syncing.
+// The library's fault word (lib.cu): raised by a kernel whose bounded barrier wait expired (tc_common.cuh).
+unsigned int* ptt_fault_word();     // host-mapped, device-visible; nullptr if it cannot be allocated
+bool ptt_fault_pending();           // plain host read, no CUDA call
+
+// Returns the launch error (if any) of the kernels enqueued so far by this call, without syncing; a device fault
+// reported by an EARLIER kernel is sticky (PTT_ERR_DEVICE_FAULT until ptt_fault_clear()).
 static inline int ptt_launch_status() {
   cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? PTT_OK : (int)e;
+  if (e != cudaSuccess) return (int)e;
+  return ptt_fault_pending() ? PTT_ERR_DEVICE_FAULT : PTT_OK;
 }
 
 // Kernel-launch counter behind ptt_launch_count() (bench.py reports it as `gpu_launches`).

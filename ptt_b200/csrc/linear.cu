@@ -5,6 +5,7 @@
 // ptt_linear_* C entry points, (b) every dense contraction of the SA-MLP and transformer paths until
 // the tcgen05 kernels take them over, and (c) the on-device cross-check for those kernels.
 #include "gemm.cuh"
+#include "ptt_b200_tuning.h"
 
 namespace {
 
@@ -117,7 +118,7 @@ __global__ void linear_pack_kernel(const float* __restrict__ w, const float* __r
 }  // namespace
 
 static int g_force_ffma = 0;
-// Test hook (not in the public header): 1 = run every contraction on the CUDA-core path.
+// Test hook (declared in include/ptt_b200_tuning.h): 1 = run every contraction on the CUDA-core path.
 extern "C" __attribute__((visibility("default"))) void ptt_debug_force_ffma(int on) { g_force_ffma = on; }
 
 int ptt_gemm_launch(const PttGemmArgs& a, cudaStream_t st) {

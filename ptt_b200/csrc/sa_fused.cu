@@ -22,6 +22,7 @@
 // in flight (SfCfg::DEEP).  BatchNorm scales of layers 2 and 3 are folded into the packed weights, so both epilogues are
 // acc + shift.  The same kernel serves CosineSimAug (pair_scalar, implicit groups of all N points: sa_mlp.cu).
 #include "sa_fused.cuh"
+#include "ptt_b200_tuning.h"
 #include "tc_common.cuh"
 
 namespace {
@@ -543,6 +544,7 @@ int sf_launch(const SaFusedArgs& a, cudaStream_t st) {
   if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
+    if (int rc = tc::tc_bind_fault(ptt_fault_word())) return rc;
     configured[dev] = true;
   }
   const long long tiles = (a.rows + SF_TM - 1) / SF_TM;

@@ -17,6 +17,7 @@
 // (value, key) pairs, max value first, min key second.  tests/ checks it against the oracle, which
 // simulates the upstream tree literally.
 #include "common.cuh"
+#include "ptt_b200_tuning.h"
 
 namespace {
 
@@ -234,7 +235,7 @@ extern "C" size_t ptt_furthest_point_sampling_workspace_bytes(int B, int N, int 
   return N > 8192 && B > 0 ? (size_t)B * N * sizeof(float) : 0;
 }
 
-// Tuning hook (not part of the public header): run FPS with an explicit (threads, points/thread).
+// Tuning hook (declared in include/ptt_b200_tuning.h): run FPS with an explicit (threads, points/thread).
 extern "C" __attribute__((visibility("default"))) int ptt_fps_variant(const float* xyz, int B, int N, int npoint, int* idx, float* new_xyz,
                                int threads, int ppt, ptt_stream_t stream) {
   cudaStream_t st = as_stream(stream);

@@ -38,11 +38,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (an error code on the host) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 26)) __trap();
+// Bounded waits.  A barrier-protocol fault must neither hang the GPU nor poison the CUDA context (__trap would): the
+// waiter that gives up raises the library's fault word -- one host-mapped word, bound to this translation unit by
+// tc_bind_fault() -- and falls through; every other waiter of the kernel sees the word at its next check and falls
+// through as well, so the kernel drains (its loops are bounded and its addresses never depend on the data it waited for)
+// and frees its TMEM.  The results are garbage, and the host knows: every entry point returns PTT_ERR_DEVICE_FAULT
+// from then on (include/ptt_b200.h: ptt_fault_status / ptt_fault_clear).
+static __device__ unsigned int* tc_fault_ptr = nullptr;
+static __device__ __forceinline__ bool tc_wait_gives_up(uint32_t spin) {
+  unsigned int* f = tc_fault_ptr;
+  if (f != nullptr && *reinterpret_cast<volatile unsigned int*>(f) != 0u) return true;
+  if (spin < (1u << 26)) return false;
+  if (f != nullptr) {
+    *reinterpret_cast<volatile unsigned int*>(f) = 1u;
+    __threadfence_system();
   }
+  return true;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
+    if ((spin & 0xffffu) == 0u && tc_wait_gives_up(spin)) return;
+  }
+}
+// host: point this translation unit's kernels at the library's fault word (idempotent; once per kernel family and device)
+static inline int tc_bind_fault(unsigned int* host_mapped_word) {
+  return (int)cudaMemcpyToSymbol(tc_fault_ptr, &host_mapped_word, sizeof(host_mapped_word));
 }
 
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)
@@ -202,7 +222,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (ok) break;
-    if (spin > (1u << 26)) __trap();
+    if (((spin + 1) & 0xffffu) == 0u && tc_wait_gives_up(spin + 1)) return;
   }
 }
 

@@ -304,6 +304,7 @@ int tc_launch(const TcParams& p, cudaStream_t st) {
   if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
+    if (int rc = tc::tc_bind_fault(ptt_fault_word())) return rc;
     configured[dev] = true;
   }
   dim3 grid(ceil_div(p.g.R, TBM), ceil_div(p.g.N, BN), p.g.batch > 0 ? p.g.batch : 1);

@@ -74,15 +74,22 @@ class HotPath:
         self.streams = None
         self.use_graph = True         # forward_host replays a captured CUDA graph
         self.overlap = True           # template branch on a second stream (False: one stream, for per-stage timing)
-        self._ws = {}                 # persistent per-stage workspaces (no allocator traffic in steady state)
+        # persistent per-stage workspaces (no allocator traffic in steady state), keyed by (scope, stage): the eager path
+        # uses scope None, every captured CUDA graph its own scope -- a graph bakes the workspace ADDRESSES in, so a
+        # workspace that a later, larger shape re-allocates must not be one an existing graph still replays into
+        self._ws = {}
+        self._ws_scope = None
         self.stage_events = None      # set to {} to record (start, end) CUDA events per stage on its stream
 
     def _workspace(self, tag, nbytes):
         need = max(int(nbytes), 16) // 4 + 4
-        ws = self._ws.get(tag)
+        key = (self._ws_scope, tag)
+        ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
+            if ws is not None and self._ws_scope is not None and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("workspace %r grew during graph capture" % (key,))
             ws = torch.empty(need, dtype=torch.float32, device=self.device)
-            self._ws[tag] = ws
+            self._ws[key] = ws
         return ws
 
     def profile(self, on=True):
@@ -288,6 +295,7 @@ class HotPath:
             static_t = template.clone()
             was_profiling = self.stage_events is not None
             self.stage_events = None
+            self._ws_scope = key                               # this graph owns its workspaces (see __init__)
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                      # warm-up: one-time kernel attribute calls, allocator pools
@@ -298,6 +306,7 @@ class HotPath:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = fwd(static_s, static_t)
+            self._ws_scope = None
             if was_profiling:
                 self.stage_events = {}
             g[key] = (graph, static_s, static_t, out)
@@ -308,84 +317,122 @@ class HotPath:
         return out
 
     # ------------------------------------------------------------------------------------------------
-    # Asynchronous host API: submit() enqueues H2D + graph replay + D2H on this instance's own stream and returns at
-    # once; collect() waits for that step's results.  Two instances used alternately (HostPipeline) overlap the
-    # copies and the serial stretches (FPS, ball query) of one step with the dense kernels of the next.
+    # Host API.  What a caller of the reference reads back per frame is the 5-float box of the best proposal
+    # (eval_tracking_utils.py:266-274), so the host entry points copy back a SELECTION of the outputs:
+    #   outputs=None   the default selection: ("best_box",) for the whole tracker forward (full=True), the final stage's
+    #                  features ("box_feats",) for the hot path alone
+    #   outputs="all"  every output tensor (hot path: 22 MB per 48-frame step)
+    #   outputs=(...)  any subset of the keys forward() / forward_full() return
     # ------------------------------------------------------------------------------------------------
-    def submit_host(self, search_host, template_host, to_host=True, after=None):
-        """Inputs: pinned CPU tensors (copied H2D) or CUDA tensors.  to_host=False leaves the results on the device
-        (collect_host then returns the graph's static output tensors).  `after`: CUDA event to wait for first."""
+    HOST_KEYS = ("search_seeds", "search_feats", "search_inds", "template_seeds", "template_feats", "template_inds",
+                 "centroid_feats", "box_centers", "box_sa_feats", "box_feats")
+    HOST_KEYS_FULL = ("search_seeds", "search_feats", "search_inds", "template_seeds", "template_feats", "template_inds",
+                      "cosine_feats", "centroid_feats", "pred_centroids_cls", "pred_centroids_votes", "votes_feats",
+                      "pred_box_center", "box_feats", "pred_box_data", "best_box", "best_idx")
+
+    def _select(self, outputs, full):
+        if outputs is None:
+            return ("best_box",) if full else ("box_feats",)
+        if isinstance(outputs, str):
+            if outputs != "all":
+                outputs = (outputs,)
+            else:
+                return self.HOST_KEYS_FULL if full else self.HOST_KEYS
+        allowed = self.HOST_KEYS_FULL if full else self.HOST_KEYS
+        for k in outputs:
+            if k not in allowed:
+                raise KeyError("unknown output %r (have: %s)" % (k, ", ".join(allowed)))
+        return tuple(outputs)
+
+    def _result_set(self, out, keys, to_host):
+        """Result buffers the selected outputs are copied into: TWO sets per (selection, placement), used alternately,
+        so the tensors a collect() returned stay untouched by the NEXT submit on this instance (they are overwritten by
+        the one after it).  Pinned host memory for to_host, device memory otherwise (the graph's static outputs
+        themselves are rewritten by every replay)."""
+        sets = getattr(self, "_result_sets", None)
+        if sets is None:
+            sets = self._result_sets = {}
+        sig = (keys, bool(to_host), tuple(tuple(out[k].shape) for k in keys))
+        if sig not in sets:
+            mk = (lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)) if to_host else torch.empty_like
+            sets[sig] = [[{k: mk(out[k]) for k in keys} for _ in range(2)], 0]
+        pair, nxt = sets[sig]
+        sets[sig][1] = nxt ^ 1
+        return pair[nxt]
+
+    def submit_host(self, search_host, template_host, to_host=True, after=None, outputs=None, full=False):
+        """Asynchronous: enqueues H2D + graph replay + the copies of the selected outputs on this instance's own stream
+        and returns at once; collect_host() waits for that step.  Inputs: pinned CPU tensors (copied H2D) or CUDA
+        tensors.  to_host=False keeps the results on the device.  `after`: CUDA event to wait for first."""
         if getattr(self, "_io_stream", None) is None:
             self._io_stream = torch.cuda.Stream(self.device)
             self._done = torch.cuda.Event()
+        keys = self._select(outputs, full)
         with torch.cuda.stream(self._io_stream):
             if after is not None:
                 self._io_stream.wait_event(after)
             search = search_host.to(self.device, non_blocking=True)
             template = template_host.to(self.device, non_blocking=True)
-            out = self.forward_graph(search, template)
-            if not to_host:
-                self._dev_out = out
-                self._done.record(self._io_stream)
-                return
-            bufs = getattr(self, "_host_out", None)
-            if bufs is None or any(tuple(bufs[k].shape) != tuple(out[k].shape) for k in self.HOST_KEYS):
-                bufs = {k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True) for k in self.HOST_KEYS}
-                self._host_out = bufs
-            for k in self.HOST_KEYS:
+            out = self.forward_graph(search, template, full=full)
+            bufs = self._result_set(out, keys, to_host)
+            for k in keys:
                 bufs[k].copy_(out[k], non_blocking=True)
+            self._last = bufs
             self._done.record(self._io_stream)
 
-    def collect_host(self, to_host=True):
+    def collect_host(self):
+        """Results of the last submit_host(): valid until the second submit_host() after it on this instance."""
         self._done.synchronize()
-        return self._host_out if to_host else self._dev_out
+        return self._last
 
-    HOST_KEYS = ("search_seeds", "search_feats", "search_inds", "template_seeds", "template_feats", "template_inds",
-                 "centroid_feats", "box_centers", "box_sa_feats", "box_feats")
-
-    def forward_host(self, search_host, template_host):
-        """The call a host-side user makes: CPU tensors in (pinned memory makes the copies asynchronous), CPU
-        tensors out (persistent pinned buffers, overwritten by the next call).  Host->device copies of the clouds
-        and device->host copies of every output are part of the call; returns after the results have landed."""
-        dev = self.device
-        search = search_host.to(dev, non_blocking=True)
-        template = template_host.to(dev, non_blocking=True)
-        out = self.forward_graph(search, template) if self.use_graph else self.forward(search, template)
-        bufs = getattr(self, "_host_out", None)
-        if bufs is None or any(tuple(bufs[k].shape) != tuple(out[k].shape) for k in self.HOST_KEYS):
-            bufs = {k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True) for k in self.HOST_KEYS}
-            self._host_out = bufs
-        for k in self.HOST_KEYS:
-            bufs[k].copy_(out[k], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return bufs
+    def forward_host(self, search_host, template_host, outputs=None, full=False):
+        """The synchronous call a host-side user makes: CPU tensors in (pinned memory makes the copies asynchronous),
+        CPU tensors out (persistent pinned buffers; see collect_host for their lifetime).  Host->device copies of the
+        clouds and device->host copies of the selected outputs are part of the call; returns after they have landed."""
+        if not self.use_graph:
+            keys = self._select(outputs, full)
+            dev = self.device
+            out = (self.forward_full if full else self.forward)(search_host.to(dev, non_blocking=True),
+                                                                template_host.to(dev, non_blocking=True))
+            bufs = self._result_set(out, keys, True)
+            for k in keys:
+                bufs[k].copy_(out[k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return bufs
+        self.submit_host(search_host, template_host, outputs=outputs, full=full)
+        return self.collect_host()
 
 
 class HostPipeline:
-    """Throughput-oriented host API: `depth` HotPath instances (own CUDA graph, workspaces, streams, pinned output
-    buffers) used round-robin, so step i+1's H2D copy and compute overlap step i's D2H copy and serial stretches.
+    """Throughput-oriented host API: `depth` HotPath instances (own CUDA graph, workspaces, streams, result buffers)
+    used round-robin, so step i+1's H2D copy and compute overlap step i's D2H copy and serial stretches.
 
         pipe = HostPipeline(state_dict)
         for search, template in frames:            # pinned CPU tensors
-            prev = pipe.push(search, template)     # results of the step submitted depth-1 pushes ago (or None)
+            prev = pipe.push(search, template)     # results of the step submitted `depth` pushes ago (None while filling)
         tail = pipe.drain()                        # remaining results, oldest first
-    """
 
-    def __init__(self, state_dict, cfg=None, device="cuda", depth=2):
+    Lifetime of a returned dict: its tensors are persistent buffers of one slot; they are rewritten by the SECOND later
+    submit on that slot, i.e. they stay valid for the next 2 * depth - 1 pushes (each slot alternates two buffer sets,
+    so the push that returns a result never writes the buffers it returns)."""
+
+    def __init__(self, state_dict, cfg=None, device="cuda", depth=2, outputs=None, full=False):
         self.slots = [HotPath(state_dict, cfg=cfg, device=device) for _ in range(depth)]
         self.pending = []          # slot indices in submission order
         self.next = 0
+        self.outputs, self.full = outputs, full
 
     def push(self, search_host, template_host, to_host=True, after=None):
         out = None
         if len(self.pending) == len(self.slots):
-            out = self.slots[self.pending.pop(0)].collect_host(to_host)
-        self.slots[self.next].submit_host(search_host, template_host, to_host=to_host, after=after)
+            out = self.slots[self.pending.pop(0)].collect_host()
+        self.slots[self.next].submit_host(search_host, template_host, to_host=to_host, after=after, outputs=self.outputs,
+                                          full=self.full)
         self.pending.append(self.next)
         self.next = (self.next + 1) % len(self.slots)
         return out
 
-    def drain(self, to_host=True):
-        outs = [self.slots[i].collect_host(to_host) for i in self.pending]
+    def drain(self):
+        outs = [self.slots[i].collect_host() for i in self.pending]
         self.pending = []
         return outs

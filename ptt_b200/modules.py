@@ -79,7 +79,62 @@ class _SharedMLP(nn.Sequential):
             self.add_module("layer%d" % i, _ConvUnit(spec[i], spec[i + 1], bn))
 
 
-class PointnetSAModuleVotes(nn.Module):
+# ------------------------------------------------------------------------------------------------
+# Packed-parameter cache and the fused / autograd switch shared by every module below
+# ------------------------------------------------------------------------------------------------
+class _PackCache:
+    """Packed parameter images are rebuilt whenever the parameters may have changed: on train() / _apply() /
+    load_state_dict(), and whenever the identity or the in-place version counter of any parameter or buffer differs
+    from what it was at pack time (optimizer.step() with frozen BatchNorm, `p.mul_()`, `load_state_dict`, a moved
+    module).  Writes that bypass the version counter (`p.data.copy_(..)`, raw-pointer writes) need `invalidate()`."""
+
+    _packed = None
+    _packed_key = None
+
+    def invalidate(self):
+        self._packed = None
+        self._packed_key = None
+
+    def _param_key(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _cached(self, build):
+        key = self._param_key()
+        if self._packed is None or self._packed_key != key:
+            self._packed = build()
+            self._packed_key = key
+        return self._packed
+
+    def train(self, mode=True):
+        self.invalidate()
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *a, **k):
+        self.invalidate()
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def _use_fused(self, *tensors):
+        """The fused C path returns tensors without an autograd graph, so it is taken only when nobody can ask for
+        gradients: eval mode, and either grad mode off (the reference's evaluation loop runs under no_grad) or neither
+        an input nor a parameter of this module requires grad.  eval() with grad enabled (frozen-BatchNorm fine-tuning,
+        saliency) therefore builds the graph through the decomposition, as the reference does."""
+        for t in tensors:
+            if t is not None and not t.is_cuda:
+                raise ops.PttError("%s runs on CUDA only (there is no CPU path)" % type(self).__name__)
+        if self.training:
+            return False
+        if not torch.is_grad_enabled():
+            return True
+        if any(t is not None and t.requires_grad for t in tensors):
+            return False
+        return not any(p.requires_grad for p in self.parameters())
+
+
+class PointnetSAModuleVotes(_PackCache, nn.Module):
     def __init__(self, *, mlp, radius=None, nsample=None, bn=True, use_xyz=True, normalize_xyz=False,
                  sample_uniformly=False, sample_method="fps"):
         super().__init__()
@@ -94,36 +149,23 @@ class PointnetSAModuleVotes(nn.Module):
         if use_xyz and len(mlp_spec) > 0:
             mlp_spec[0] += 3          # in place, like the reference (pointnet2_modules.py:51-53)
         self.mlp_module = _SharedMLP(mlp_spec, bn)
-        self._packed = None
 
-    # packed parameters are rebuilt whenever the module may have changed
-    def train(self, mode=True):
-        self._packed = None
-        return super().train(mode)
-
-    def _load_from_state_dict(self, *a, **k):
-        self._packed = None
-        return super()._load_from_state_dict(*a, **k)
-
-    def _apply(self, fn, *a, **k):
-        self._packed = None
-        return super()._apply(fn, *a, **k)
+    def _build_packed(self):
+        ws, scales, shifts = [], [], []
+        for unit in self.mlp_module:
+            w = unit.conv.weight.detach()
+            ws.append(w.reshape(w.shape[0], w.shape[1]))
+            if hasattr(unit, "normlayer"):
+                bn = unit.normlayer.bn
+                s, t = ops.fold_batchnorm(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
+            else:
+                s, t = None, unit.conv.bias.detach()
+            scales.append(s)
+            shifts.append(t)
+        return ops.PackedSAMlp(ws, scales, shifts)
 
     def _pack(self):
-        if self._packed is None:
-            ws, scales, shifts = [], [], []
-            for unit in self.mlp_module:
-                w = unit.conv.weight.detach()
-                ws.append(w.reshape(w.shape[0], w.shape[1]))
-                if hasattr(unit, "normlayer"):
-                    bn = unit.normlayer.bn
-                    s, t = ops.fold_batchnorm(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
-                else:
-                    s, t = None, unit.conv.bias.detach()
-                scales.append(s)
-                shifts.append(t)
-            self._packed = ops.PackedSAMlp(ws, scales, shifts)
-        return self._packed
+        return self._cached(self._build_packed)
 
     def _sample(self, xyz, features, npoint):
         if self.sample_method == "fps":
@@ -145,9 +187,7 @@ class PointnetSAModuleVotes(nn.Module):
         else:
             assert inds.shape[1] == npoint
         inds32 = inds.to(torch.int32).contiguous()
-        fused = (not self.training) and self.use_xyz and not (torch.is_grad_enabled() and (
-            xyz.requires_grad or (features is not None and features.requires_grad)))
-        if fused:
+        if self.use_xyz and self._use_fused(xyz, features):
             new_xyz = torch.gather(xyz, 1, inds32.long().unsqueeze(-1).expand(-1, -1, 3))
             idx = ops.ball_query(new_xyz, xyz, self.radius, self.nsample)
             feats_pm = ops.cm_to_pm(features.contiguous()) if features is not None else None
@@ -173,7 +213,7 @@ class PointnetSAModuleVotes(nn.Module):
         return new_xyz, new_features, inds.to(torch.int64)
 
 
-class TransformerBlock(nn.Module):
+class TransformerBlock(_PackCache, nn.Module):
     VARIANT = 0
 
     def __init__(self, d_points, d_model, k, **kwargs):
@@ -187,33 +227,17 @@ class TransformerBlock(nn.Module):
         self.w_vs = nn.Linear(d_model, d_model, bias=False)
         self.k = k
         self.return_attn = True      # the reference returns (res, attn); its callers use only [0]
-        self._packed = None
-
-    def train(self, mode=True):
-        self._packed = None
-        return super().train(mode)
-
-    def _load_from_state_dict(self, *a, **k):
-        self._packed = None
-        return super()._load_from_state_dict(*a, **k)
-
-    def _apply(self, fn, *a, **k):
-        self._packed = None
-        return super()._apply(fn, *a, **k)
 
     def _pack(self):
-        if self._packed is None:
-            sd = {k: v.detach() for k, v in self.state_dict().items()}
-            self._packed = ops.PackedTransformer(sd, self.k, self.VARIANT)
-        return self._packed
+        return self._cached(lambda: ops.PackedTransformer({k: v.detach() for k, v in self.state_dict().items()},
+                                                          self.k, self.VARIANT))
 
     def forward(self, xyz, features):
         if not xyz.is_cuda:
             raise ops.PttError("ptt_b200.TransformerBlock runs on CUDA only (there is no CPU path)")
         xyz = xyz.contiguous()
         features = features.contiguous()
-        fused = (not self.training) and not (torch.is_grad_enabled() and (xyz.requires_grad or features.requires_grad))
-        if fused:
+        if self._use_fused(xyz, features):
             r = ops.transformer_block_fwd(self._pack(), xyz, features, want_attn=self.return_attn)
             return r if self.return_attn else (r, None)
 
@@ -241,7 +265,7 @@ class TransformerBlockOffset(TransformerBlock):
     VARIANT = 1
 
 
-class TransformerBlockSTD(nn.Module):
+class TransformerBlockSTD(_PackCache, nn.Module):
     """Dense n x n dot-product attention (variants.py:12-40); same constructor, forward and state_dict."""
 
     def __init__(self, d_points, d_model, k, **kwargs):
@@ -253,29 +277,14 @@ class TransformerBlockSTD(nn.Module):
         self.w_ks = nn.Linear(d_model, d_model, bias=False)
         self.w_vs = nn.Linear(d_model, d_model, bias=False)
         self.k = k
-        self._packed = None
-
-    def train(self, mode=True):
-        self._packed = None
-        return super().train(mode)
-
-    def _load_from_state_dict(self, *a, **k):
-        self._packed = None
-        return super()._load_from_state_dict(*a, **k)
-
-    def _apply(self, fn, *a, **k):
-        self._packed = None
-        return super()._apply(fn, *a, **k)
 
     def forward(self, xyz, features):
         if not xyz.is_cuda:
             raise ops.PttError("ptt_b200.TransformerBlockSTD runs on CUDA only (there is no CPU path)")
         xyz, features = xyz.contiguous(), features.contiguous()
-        fused = (not self.training) and not (torch.is_grad_enabled() and (xyz.requires_grad or features.requires_grad))
-        if fused:
-            if self._packed is None:
-                self._packed = ops.PackedTransformerSTD({k: v.detach() for k, v in self.state_dict().items()})
-            return ops.transformer_std_fwd(self._packed, xyz, features, want_attn=True)
+        if self._use_fused(xyz, features):
+            packed = self._cached(lambda: ops.PackedTransformerSTD({k: v.detach() for k, v in self.state_dict().items()}))
+            return ops.transformer_std_fwd(packed, xyz, features, want_attn=True)
         pre = features
         x = self.fc1(features)
         q, k, v = self.w_qs(x), self.w_ks(x), self.w_vs(x)
@@ -302,33 +311,17 @@ def _vector_attention(q, kk, v, pos, fc_gamma):
     return torch.einsum("bmnf,bmnf->bmf", attn, v + pos), attn
 
 
-class _PackedModule(nn.Module):
-    """Drops the packed parameter images whenever the parameters may have changed."""
-
-    def __init__(self):
-        super().__init__()
-        self._packed = None
-
-    def train(self, mode=True):
-        self._packed = None
-        return super().train(mode)
-
-    def _load_from_state_dict(self, *a, **k):
-        self._packed = None
-        return super()._load_from_state_dict(*a, **k)
-
-    def _apply(self, fn, *a, **k):
-        self._packed = None
-        return super()._apply(fn, *a, **k)
-
+class _PackedModule(_PackCache, nn.Module):
     def _sd(self):
         return {k: v.detach() for k, v in self.state_dict().items()}
 
     def _fused(self, *tensors):
-        for t in tensors:
-            if not t.is_cuda:
-                raise ops.PttError("%s runs on CUDA only (there is no CPU path)" % type(self).__name__)
-        return (not self.training) and not (torch.is_grad_enabled() and any(t.requires_grad for t in tensors))
+        if not self._use_fused(*tensors):
+            return False
+        key = self._param_key()            # the blocks below build their images inline under `if self._packed is None`
+        if self._packed_key != key:
+            self._packed, self._packed_key = None, key
+        return True
 
     def _core_layers(self, d_points, d_model, gamma_dim=None):
         g = gamma_dim or d_model

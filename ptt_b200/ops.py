@@ -55,6 +55,25 @@ class _DeviceGuard:
 
 _F, _I = torch.float32, torch.int32
 
+# The tcgen05 contractions split every fp32 operand into two fp16 halves (hi + lo, ~22 significant bits) with SATURATING
+# conversions: |x| > 65504 would clamp silently.  Weights are checked once, at pack time (one device->host read; the
+# pack calls synchronise anyway); anything beyond SPLIT_MAX -- far outside what a BatchNorm-folded PTT layer holds -- is
+# refused instead of being computed wrongly.  Small magnitudes degrade gracefully: the lo half goes subnormal below
+# |x| ~ 0.12, which bounds the ABSOLUTE representation error of an operand by 2^-25 (3e-8), not its relative error.
+SPLIT_MAX = 3.0e4
+
+
+def check_split_range(what, *tensors):
+    worst = 0.0
+    for t in tensors:
+        if t is not None and t.numel():
+            worst = max(worst, float(t.detach().abs().max()))
+    if not worst < SPLIT_MAX:
+        raise PttError("%s: largest magnitude %.3g is outside the fp16 hi/lo split range (|w| < %.0f) of the tensor-core "
+                       "path; rescale the layer (fold the factor into the next layer or the BatchNorm scale)"
+                       % (what, worst, SPLIT_MAX))
+
+
 
 def _workspace(nbytes, dev):
     return torch.empty(max(int(nbytes), 16) // 4 + 4, dtype=_F, device=dev)
@@ -237,6 +256,7 @@ class PackedLinear:
     def __init__(self, weight, bias=None):
         _req(weight, _F, 2, "weight")
         self.cout, self.k = weight.shape
+        check_split_range("linear weight", weight)
         L = _lib.lib()
         with _DeviceGuard(weight.device):
             self.params = torch.empty(L.ptt_linear_params_floats(self.k, self.cout), dtype=_F, device=weight.device)
@@ -329,6 +349,8 @@ class PackedSAMlp:
 
         scales = [s.contiguous() if s is not None else None for s in (scales or [None] * self.n_layers)]
         shifts = [s.contiguous() if s is not None else None for s in (shifts or [None] * self.n_layers)]
+        check_split_range("SA layer weight (BatchNorm scale folded)",
+                          *[w * sc[:, None] if sc is not None else w for w, sc in zip(ws, scales)])
         with _DeviceGuard(dev):
             self.params = torch.empty(n, dtype=_F, device=dev)
             check(L.ptt_sa_pack_params(self.C, self.n_layers, self.h_dims, arr(ws), arr(scales), arr(shifts),
@@ -429,6 +451,7 @@ class PackedTransformer:
 
     def __init__(self, sd, k, variant=0):
         ts = [_req(sd[key].contiguous(), _F, sd[key].dim(), key) for key in TRANSFORMER_KEYS]
+        check_split_range("transformer block weight", *[t for t in ts if t.dim() == 2])
         self.d_model, self.d_points = ts[0].shape
         self.k = int(k)
         self.variant = int(variant)
@@ -538,6 +561,7 @@ class PackedTransformerSTD:
 
     def __init__(self, sd):
         ts = [_req(sd[key].contiguous(), _F, sd[key].dim(), key) for key in STD_KEYS]
+        check_split_range("transformer block weight", *[t for t in ts if t.dim() == 2])
         self.d_model, self.d_points = ts[0].shape
         dev = ts[0].device
         L = _lib.lib()

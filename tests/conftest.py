@@ -14,7 +14,7 @@ GOLDEN = os.path.join(REPO, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "reference: needs the reference tree at /root/reference (authoring container only)")
+    config.addinivalue_line("markers", "reference: needs the reference tree (/root/reference, or oracle/_ref staged by oracle/make_ref.sh)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -25,7 +25,7 @@ def pytest_collection_modifyitems(config, items):
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
         if "reference" in item.keywords and not refload.available():
-            item.add_marker(pytest.mark.skip(reason="/root/reference not present"))
+            item.add_marker(pytest.mark.skip(reason="no reference tree (/root/reference or oracle/_ref)"))
 
 
 @pytest.fixture(scope="session")

@@ -10,10 +10,11 @@ import torch
 from conftest import REPO
 
 HEADER = os.path.join(REPO, "include", "ptt_b200.h")
+TUNING_HEADER = os.path.join(REPO, "include", "ptt_b200_tuning.h")
 
 
-def declared_symbols():
-    text = open(HEADER).read()
+def declared_symbols(header=HEADER):
+    text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return re.findall(r"PTT_API\s+[\w\s\*]+?\b(ptt_\w+)\s*\(", text)
 
@@ -52,6 +53,32 @@ def test_binding_table_matches_header(built_lib):
         assert n == len(argtypes), "%s: header has %d arguments, binding %d" % (name, n, len(argtypes))
     assert _lib.version().startswith("ptt_b200 ") and _lib.version().endswith("sm_100a")
     assert _lib.lib().ptt_error_string(-3).decode().startswith("workspace")
+
+
+def test_tuning_surface_is_declared_bound_and_unused_by_the_product(built_lib):
+    """Every exported symbol is declared in one of the two headers (no undeclared hooks), the process-wide tuning
+    switches live in ptt_b200_tuning.h, and nothing under ptt_b200/ calls them."""
+    import glob
+    import subprocess
+    from ptt_b200 import _lib
+    tuning = declared_symbols(TUNING_HEADER)
+    assert set(tuning) == set(_lib.TUNING_SIGNATURES) and not set(tuning) & set(declared_symbols())
+    out = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln and ln.split()[-1].startswith("ptt_")}
+    assert exported == set(declared_symbols()) | set(tuning), exported ^ (set(declared_symbols()) | set(tuning))
+    for path in glob.glob(os.path.join(REPO, "ptt_b200", "**", "*.py"), recursive=True):
+        if path.endswith("_lib.py"):
+            continue
+        text = open(path).read()
+        for name in tuning:
+            assert name not in text, "%s uses the tuning hook %s" % (path, name)
+
+
+def test_fault_word_is_quiet_without_a_device(built_lib):
+    from ptt_b200 import _lib
+    assert _lib.fault_status() == 0          # never allocates, never touches CUDA
+    _lib.fault_clear()
+    assert _lib.lib().ptt_error_string(-4).decode().startswith("a kernel of this library gave up")
 
 
 def test_workspace_queries_are_host_only(built_lib):

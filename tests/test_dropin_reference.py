@@ -1,4 +1,4 @@
-"""Authoring container only (needs /root/reference): the drop-in seam really is where the reference looks.
+"""Needs the reference tree (/root/reference, or the copy oracle/make_ref.sh stages): the drop-in seam really is where the reference looks.
 No GPU here, so this checks resolution / registration / state_dict compatibility, not compute."""
 import os
 import subprocess
@@ -7,11 +7,13 @@ import sys
 import pytest
 
 from conftest import REPO
+from oracle import refload
 
 SCRIPT = r'''
 import os, sys
 repo = sys.argv[1]
-sys.path[:0] = [repo, os.path.join(repo, "oracle", "shims"), "/root/reference"]   # thop / easydict shims only
+ref = sys.argv[2]
+sys.path[:0] = [repo, os.path.join(repo, "oracle", "shims"), ref]   # thop / easydict shims only
 import torch
 torch.Tensor.cuda = lambda self, *a, **k: self
 torch.nn.Module.cuda = lambda self, *a, **k: self
@@ -27,7 +29,7 @@ assert pm.PointnetSAModuleVotes is m.PointnetSAModuleVotes and tb.__all__["Trans
 # a whole tracker built by the reference's own factory now contains our modules, with the reference's state_dict
 import yaml
 from easydict import EasyDict
-cfg = EasyDict(yaml.safe_load(open("/root/reference/tools/cfgs/kitti_models/ptt.yaml")))
+cfg = EasyDict(yaml.safe_load(open(os.path.join(ref, "tools/cfgs/kitti_models/ptt.yaml"))))
 class DS:
     training = False; class_names = ["Car"]; grid_size = voxel_size = point_cloud_range = None
     class point_feature_encoder: num_point_features = 3
@@ -39,7 +41,7 @@ assert isinstance(net.box_voting_head.vote_aggregation, m.PointnetSAModuleVotes)
 ours = {k: tuple(v.shape) for k, v in net.state_dict().items()}
 # the same model with the reference's own classes
 pm.PointnetSAModuleVotes = ref_sa; tb.__all__["TransformerBlock"] = ref_tr
-cfg = EasyDict(yaml.safe_load(open("/root/reference/tools/cfgs/kitti_models/ptt.yaml")))
+cfg = EasyDict(yaml.safe_load(open(os.path.join(ref, "tools/cfgs/kitti_models/ptt.yaml"))))
 theirs = {k: tuple(v.shape) for k, v in build_network(cfg.MODEL, 1, DS()).state_dict().items()}
 assert ours == theirs, set(ours) ^ set(theirs)
 print("OK", len(ours), sum(1 for _ in net.parameters()))
@@ -48,7 +50,7 @@ print("OK", len(ours), sum(1 for _ in net.parameters()))
 
 @pytest.mark.reference
 def test_reference_resolves_ext_and_registries_to_ptt_b200():
-    r = subprocess.run([sys.executable, "-c", SCRIPT, REPO], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", SCRIPT, REPO, refload.REFERENCE_ROOT], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().startswith("OK 175")          # 175 state_dict keys
 
@@ -56,7 +58,8 @@ def test_reference_resolves_ext_and_registries_to_ptt_b200():
 REGISTRY_SCRIPT = r'''
 import os, sys
 repo = sys.argv[1]
-sys.path[:0] = [repo, os.path.join(repo, "oracle", "shims"), "/root/reference"]
+ref = sys.argv[2]
+sys.path[:0] = [repo, os.path.join(repo, "oracle", "shims"), ref]
 import torch
 torch.Tensor.cuda = lambda self, *a, **k: self
 torch.nn.Module.cuda = lambda self, *a, **k: self
@@ -82,6 +85,6 @@ print("OK", n)
 
 @pytest.mark.reference
 def test_every_registered_transformer_block_has_a_state_dict_compatible_twin():
-    r = subprocess.run([sys.executable, "-c", REGISTRY_SCRIPT, REPO], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", REGISTRY_SCRIPT, REPO, refload.REFERENCE_ROOT], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip() == "OK 9"

@@ -235,30 +235,126 @@ def test_hot_path_graph_replay_matches_eager_and_host_api():
         torch.cuda.synchronize()
         for k in eager:
             assert torch.equal(eager[k], replay[k]), k          # same kernels, same order: bit-identical
-        host = hp.forward_host(search.cpu().pin_memory(), template.cpu().pin_memory())
-        for k in eager:
+        host = hp.forward_host(search.cpu().pin_memory(), template.cpu().pin_memory(), outputs="all")
+        assert set(host) == set(hp.HOST_KEYS)
+        for k in host:
             assert torch.equal(eager[k].cpu(), host[k]), k
+        dflt = hp.forward_host(search.cpu().pin_memory(), template.cpu().pin_memory())     # default selection
+        assert list(dflt) == ["box_feats"] and torch.equal(dflt["box_feats"], eager["box_feats"].cpu())
         outs.append(eager["box_feats"])
     assert not torch.equal(outs[0], outs[1])
+    with pytest.raises(KeyError):
+        hp.forward_host(search.cpu().pin_memory(), template.cpu().pin_memory(), outputs=("no_such_output",))
+
+
+def test_graphs_of_different_shapes_keep_their_own_workspaces():
+    """A graph captured for a small batch must replay correctly after a LARGER shape has been run (eagerly and as a
+    graph) on the same HotPath: every captured graph owns its workspaces (a re-allocated shared workspace
+    left the first graph replaying into freed memory)."""
+    sd = synth.hot_path_state_dict(0)
+    hp = hotpath.HotPath(sd, device=DEV)
+    small = (g(synth.make_clouds(2, 1024, 610, "dense")), g(synth.make_clouds(2, 512, 611, "dense", role="template")))
+    big = (g(synth.make_clouds(12, 1024, 612, "dense")), g(synth.make_clouds(12, 512, 613, "dense", role="template")))
+    first = {k: v.clone() for k, v in hp.forward_graph(*small).items()}
+    hp(*big)                                                   # eager, larger: grows the eager-scope workspaces
+    big_out = {k: v.clone() for k, v in hp.forward_graph(*big).items()}
+    junk = [torch.full((1 << 22,), float("nan"), device=DEV) for _ in range(8)]     # recycle whatever was freed
+    again = hp.forward_graph(*small)
+    torch.cuda.synchronize()
+    for k in first:
+        assert torch.equal(first[k], again[k]), k
+    eager_big = hp(*big)
+    for k in big_out:
+        assert torch.equal(big_out[k], eager_big[k]), k
+    del junk
 
 
 def test_host_pipeline_matches_synchronous_api():
+    """Results come back in submission order and -- WITHOUT cloning them -- survive the step that the returning push
+    itself enqueued on the same slot (push() used to hand out buffers the in-flight step was overwriting)."""
     sd = synth.hot_path_state_dict(0)
     hp = hotpath.HotPath(sd, device=DEV)
-    pipe = hotpath.HostPipeline(sd, device=DEV, depth=2)
-    batches = [(t(synth.make_clouds(3, 1024, 700 + i, "dense")).pin_memory(),
-                t(synth.make_clouds(3, 512, 750 + i, "dense", role="template")).pin_memory()) for i in range(5)]
-    want = [{k: v.clone() for k, v in hp.forward_host(s, tm).items()} for s, tm in batches]
-    got = []
-    for s, tm in batches:
-        r = pipe.push(s, tm)
-        if r is not None:
-            got.append({k: v.clone() for k, v in r.items()})
-    got += [{k: v.clone() for k, v in r.items()} for r in pipe.drain()]
-    assert len(got) == len(want)
-    for a, b in zip(got, want):
-        for k in a:
-            assert torch.equal(a[k], b[k]), k
+    for outputs in ("all", None, ("box_feats", "search_inds")):
+        pipe = hotpath.HostPipeline(sd, device=DEV, depth=2, outputs=outputs)
+        batches = [(t(synth.make_clouds(3, 1024, 700 + i, "dense")).pin_memory(),
+                    t(synth.make_clouds(3, 512, 750 + i, "dense", role="template")).pin_memory()) for i in range(6)]
+        want = [{k: v.clone() for k, v in hp.forward_host(s, tm, outputs=outputs).items()} for s, tm in batches]
+        n_got = 0
+        for s, tm in batches:
+            r = pipe.push(s, tm)
+            if r is not None:
+                torch.cuda.synchronize()        # the step just submitted on r's slot has finished: r must be intact
+                assert set(r) == set(want[n_got])
+                for k in r:
+                    assert torch.equal(r[k], want[n_got][k]), (outputs, n_got, k)
+                n_got += 1
+        for r in pipe.drain():
+            for k in r:
+                assert torch.equal(r[k], want[n_got][k]), (outputs, n_got, k)
+            n_got += 1
+        assert n_got == len(want)
+        for to_host in (False,):                # device-resident results follow the same rotation
+            r0 = None
+            for i, (s, tm) in enumerate(batches[:4]):
+                r = pipe.push(s.to(DEV), tm.to(DEV), to_host=to_host)
+                if r is not None and r0 is None:
+                    torch.cuda.synchronize()
+                    r0 = {k: v.clone() for k, v in r.items()}
+                    for k in r0:
+                        assert r[k].is_cuda and torch.equal(r[k].cpu(), want[0][k]), k
+            pipe.drain()
+
+
+def test_eval_mode_with_grad_enabled_builds_the_graph():
+    """eval() + grad enabled (frozen-BatchNorm fine-tuning, saliency) must not take the fused path, whose
+    outputs carry no autograd graph; under no_grad the fused path is kept and both agree."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sa = modules.PointnetSAModuleVotes(mlp=[0, 64, 64, 128], radius=0.3, nsample=32, normalize_xyz=True).to(DEV).eval()
+    tr = modules.TransformerBlock(128, 64, 8).to(DEV).eval()
+    xyz = g(synth.make_clouds(2, 256, 31, "dense"))
+    with torch.no_grad():
+        nx0, f0, _ = sa(xyz, None, 64)
+        r0, _ = tr(nx0, f0.transpose(1, 2).contiguous())
+    assert not f0.requires_grad
+    nx, f, _ = sa(xyz, None, 64)                        # grad mode on, parameters require grad
+    r, _ = tr(nx, f.transpose(1, 2).contiguous())
+    assert f.requires_grad and r.requires_grad
+    r.square().mean().backward()
+    assert sa.mlp_module.layer0.conv.weight.grad is not None and tr.fc_gamma[0].weight.grad is not None
+    np.testing.assert_allclose(f.detach().cpu().numpy(), f0.cpu().numpy(), **FP_TOL)
+    np.testing.assert_allclose(r.detach().cpu().numpy(), r0.cpu().numpy(), **FP_TOL)
+    # frozen parameters + grad mode on + inputs without grad -> nobody can ask for a gradient: fused path again
+    for p in list(sa.parameters()) + list(tr.parameters()):
+        p.requires_grad_(False)
+    _, f2, _ = sa(xyz, None, 64)
+    assert not f2.requires_grad and torch.equal(f2, f0)
+
+
+def test_packed_weights_follow_in_place_updates():
+    """an in-place parameter update in eval mode (optimizer step with frozen BN, EMA swap through copy_)
+    must not leave a stale packed image in use."""
+    tr = modules.TransformerBlock(32, 64, 4).to(DEV).eval()
+    sa = modules.PointnetSAModuleVotes(mlp=[0, 16, 32], radius=0.5, nsample=8, normalize_xyz=True).to(DEV).eval()
+    xyz = g(synth.make_clouds(2, 64, 33, "dense", role="template"))
+    feats = g(synth.features((2, 64, 32), seed=34))
+    with torch.no_grad():
+        a0, _ = tr(xyz, feats)
+        _, s0, _ = sa(xyz, None, 16)
+        tr.fc2.weight.mul_(2.0)
+        sa.mlp_module.layer1.normlayer.bn.running_var.fill_(4.0)
+        a1, _ = tr(xyz, feats)
+        _, s1, _ = sa(xyz, None, 16)
+        fresh = modules.TransformerBlock(32, 64, 4).to(DEV).eval()
+        fresh.load_state_dict(tr.state_dict())
+        assert torch.equal(a1, fresh(xyz, feats)[0]) and not torch.equal(a0, a1)
+        fresh_sa = modules.PointnetSAModuleVotes(mlp=[0, 16, 32], radius=0.5, nsample=8, normalize_xyz=True).to(DEV).eval()
+        fresh_sa.load_state_dict(sa.state_dict())
+        assert torch.equal(s1, fresh_sa(xyz, None, 16)[1]) and not torch.equal(s0, s1)
+        tr.fc2.bias.data.add_(1.0)              # .data bypasses the version counter: explicit invalidate()
+        tr.invalidate()
+        a2, _ = tr(xyz, feats)
+        np.testing.assert_allclose(a2.cpu().numpy(), (a1 + 1.0).cpu().numpy(), **FP_TOL)
 
 
 @pytest.mark.parametrize("shape", [(3, 128, 256, 512), (2, 100, 32, 64), (1, 1024, 64, 128), (4, 37, 24, 48)])
