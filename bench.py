@@ -97,12 +97,14 @@ def algorithmic_bytes(a):
     out = {}
     for tag, n0, npts in (("search", a.nsearch, cfgs["npoints_search"]), ("template", a.ntemplate, cfgs["npoints_template"])):
         n = n0
+        bq = 0.0
         for l in range(3):
             m = npts[l]
             if l == 0:
                 out["%s.sa1.fps" % tag] = 12.0 * n + 16.0 * m
-            out["%s.sa%d.ball_query" % (tag, l + 1)] = 12.0 * n + 12.0 * m + 4.0 * m * 32
+            bq += 12.0 * n + 12.0 * m + 4.0 * m * 32
             n = m
+        out["%s.ball_query" % tag] = bq            # the three levels of a branch are ONE launch (ptt_ball_query_nested)
     ns3 = cfgs["npoints_search"][2]
     nbox = cfgs.get("box_npoint", 64)
     out["box.sa.fps"] = 12.0 * ns3 + 16.0 * nbox

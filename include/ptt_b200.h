@@ -94,6 +94,13 @@ PTT_API int ptt_gather_points_grad(const float* grad_out, const int* idx, int B,
  *     d2 < radius^2 (fp32), tail padded with the first hit, all-zero row when there is none. */
 PTT_API int ptt_ball_query(const float* new_xyz, const float* xyz, int B, int N, int M, float radius,
                    int nsample, int* idx, ptt_stream_t stream);
+/*     The ball queries of ALL set-abstraction layers of a backbone branch in one launch.  Layers after the first
+ *     sample with 'sequence' = arange(npoint) (pointnet2_modules.py:70-71; ptt.yaml SAMPLE_METHOD), so with
+ *     samples (B,M_0,3) = xyz gathered by the first layer's FPS, level l queries the centres samples[:, :M_l] against
+ *     the cloud xyz (B,N,3) for l = 0 and samples[:, :M_{l-1}] for l >= 1 (M_l non-increasing, levels <= 4):
+ *     idx[l] (B,M_l,nsample_l), each exactly what ptt_ball_query returns for that pair.  h_* are HOST arrays. */
+PTT_API int ptt_ball_query_nested(const float* xyz, const float* samples, int B, int N, int levels, const int* h_M,
+                          const float* h_radius, const int* h_nsample, int* const* h_idx, ptt_stream_t stream);
 
 /* a4  _ext.group_points(points, idx)                                 pointnet2_utils.py:237
  *     points (B,C,N), idx (B,M,K) -> out (B,C,M,K) */

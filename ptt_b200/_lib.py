@@ -28,6 +28,7 @@ SIGNATURES = {
     "ptt_gather_points": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "ptt_gather_points_grad": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "ptt_ball_query": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P]),
+    "ptt_ball_query_nested": (c_int, [_P, _P, c_int, c_int, c_int, _IP, ctypes.POINTER(c_float), _IP, _PP, _P]),
     "ptt_group_points": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "ptt_group_points_grad": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "ptt_three_nn": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),

@@ -120,18 +120,23 @@ class HotPath:
             return False
 
     # a6: one set-abstraction layer (pointnet2_modules.py:57-90), point-major in / out
-    def _sa_layer(self, packed, xyz, feats_pm, npoint, radius, nsample, method, want_cm=False, tag="sa"):
+    def _sa_layer(self, packed, xyz, feats_pm, npoint, radius, nsample, method, want_cm=False, tag="sa", pre=None):
+        """pre = (inds, new_xyz, idx): sampling and ball query already done (backbone_branch answers the queries of all
+        three layers with one launch right after the FPS)."""
         c = self.cfg
-        if method == "fps":
-            with self._Stage(self, tag + ".fps"):
-                inds, new_xyz = ops.furthest_point_sampling(xyz, npoint, return_new_xyz=True)
-        elif method in ("sequence", "rs"):
-            inds = None                                    # arange(npoint): the centres are a prefix
-            new_xyz = xyz[:, :npoint].contiguous()
+        if pre is not None:
+            inds, new_xyz, idx = pre
         else:
-            raise NotImplementedError(method)
-        with self._Stage(self, tag + ".ball_query"):
-            idx = ops.ball_query(new_xyz, xyz, radius, nsample)
+            if method == "fps":
+                with self._Stage(self, tag + ".fps"):
+                    inds, new_xyz = ops.furthest_point_sampling(xyz, npoint, return_new_xyz=True)
+            elif method in ("sequence", "rs"):
+                inds = None                                    # arange(npoint): the centres are a prefix
+                new_xyz = xyz[:, :npoint].contiguous()
+            else:
+                raise NotImplementedError(method)
+            with self._Stage(self, tag + ".ball_query"):
+                idx = ops.ball_query(new_xyz, xyz, radius, nsample)
         ws = self._workspace(tag, packed.workspace_bytes(xyz.shape[0], xyz.shape[1], npoint, nsample))
         with self._Stage(self, tag + ".mlp"):
             out_pm, out_cm = ops.sa_mlp_fwd(packed, xyz, feats_pm, new_xyz, idx, radius, c["normalize_xyz"],
@@ -143,9 +148,23 @@ class HotPath:
         c = self.cfg
         xyz, feats = pts, None
         inds = []
+        methods = c["sample_methods"]
+        pre = [None, None, None]
+        if methods[0] == "fps" and all(m in ("sequence", "rs") for m in methods[1:]) and \
+                all(npoints[l] <= npoints[l - 1] for l in (1, 2)):
+            # The shipped configuration (ptt.yaml SAMPLE_METHOD): layers 2-3 take arange(npoint), so every layer's centres
+            # are a prefix of the FPS order and every later cloud is the previous prefix.  One FPS, then ONE launch for the
+            # ball queries of all three layers: they leave the critical path of layers 2-3.
+            with self._Stage(self, tag + ".sa1.fps"):
+                inds0, samples = ops.furthest_point_sampling(pts, npoints[0], return_new_xyz=True)
+            with self._Stage(self, tag + ".ball_query"):
+                idxs = ops.ball_query_nested(pts, samples, npoints, c["radii"], c["nsamples"])
+            for l in range(3):
+                ctr = samples if l == 0 else samples[:, :npoints[l]].contiguous()
+                pre[l] = (inds0 if l == 0 else None, ctr, idxs[l])
         for l in range(3):
             xyz, feats, _, i = self._sa_layer(self.sa[l], xyz, feats, npoints[l], c["radii"][l], c["nsamples"][l],
-                                              c["sample_methods"][l], tag="%s.sa%d" % (tag, l + 1))
+                                              methods[l], tag="%s.sa%d" % (tag, l + 1), pre=pre[l])
             inds.append(i)
         B, n3, cdim = feats.shape
         feat_pm = self.cov_final(feats.reshape(B * n3, cdim)).reshape(B, n3, -1)        # :46 (1x1 Conv1d == row linear)

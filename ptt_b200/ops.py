@@ -155,6 +155,31 @@ def ball_query(new_xyz, xyz, radius, nsample):
     return idx
 
 
+def ball_query_nested(xyz, samples, npoints, radii, nsamples):
+    """The ball queries of every set-abstraction layer of a backbone branch in one launch (ptt_ball_query_nested):
+    xyz (B,N,3), samples (B,npoints[0],3) = xyz in FPS order; level l: centres samples[:, :npoints[l]] against xyz
+    (l = 0) or samples[:, :npoints[l-1]].  Returns [idx_l (B,npoints[l],nsamples[l]) int32]."""
+    _req(xyz, _F, 3, "xyz"), _req(samples, _F, 3, "samples")
+    dev = _same_device(xyz, samples)
+    B, N, _ = xyz.shape
+    L = len(npoints)
+    if not (1 <= L <= 4) or len(radii) != L or len(nsamples) != L:
+        raise PttError("ball_query_nested: 1..4 levels with one radius / nsample each")
+    if samples.shape[0] != B or samples.shape[1] != npoints[0] or samples.shape[2] != 3 or xyz.shape[2] != 3:
+        raise PttError("ball_query_nested: samples must be (B,npoints[0],3)")
+    if any(npoints[l] > npoints[l - 1] for l in range(1, L)) or min(npoints) < 1 or min(nsamples) < 1:
+        raise PttError("ball_query_nested: npoints must be non-increasing and positive")
+    with _DeviceGuard(dev):
+        outs = [torch.empty(B, int(npoints[l]), int(nsamples[l]), dtype=_I, device=dev) for l in range(L)]
+        h_m = (ctypes.c_int * L)(*[int(v) for v in npoints])
+        h_r = (ctypes.c_float * L)(*[float(v) for v in radii])
+        h_ns = (ctypes.c_int * L)(*[int(v) for v in nsamples])
+        h_out = (ctypes.c_void_p * L)(*[o.data_ptr() for o in outs])
+        check(_lib.lib().ptt_ball_query_nested(_ptr(xyz), _ptr(samples), B, N, L, h_m, h_r, h_ns, h_out, _stream()),
+              "ptt_ball_query_nested")
+    return outs
+
+
 def group_points(points, idx):
     _req(points, _F, 3, "points"), _req(idx, _I, 3, "idx")
     dev = _same_device(points, idx)

@@ -113,6 +113,23 @@ def test_ball_query_vs_oracle(n, m, r, ns, kind):
     assert (got[:, -1] == 0).all()
 
 
+@pytest.mark.parametrize("n,npoints,kind", [(1024, (512, 256, 128), "dense"), (512, (512, 256, 128), "sparse"),
+                                            (300, (200, 200, 7), "dense"), (64, (33,), "dense")])
+def test_ball_query_nested_equals_the_single_queries(n, npoints, kind):
+    """ptt_ball_query_nested (all levels of a backbone branch in one launch) == one ptt_ball_query per level == oracle."""
+    xyz = synth.make_clouds(5, n, 230 + n, kind)
+    samples = np.take_along_axis(xyz, cops.furthest_point_sampling(t(xyz), npoints[0]).long().numpy()[:, :, None], 1)
+    radii, nss = (0.3, 0.5, 0.7)[:len(npoints)], (32, 16, 5)[:len(npoints)]
+    got = ops.ball_query_nested(g(xyz), g(samples), npoints, radii, nss)
+    src = xyz
+    for l, m in enumerate(npoints):
+        ctr = np.ascontiguousarray(samples[:, :m])
+        want = cops.ball_query(t(ctr), t(src), radii[l], nss[l]).numpy()
+        assert np.array_equal(got[l].cpu().numpy(), want), l
+        assert np.array_equal(ops.ball_query(g(ctr), g(src), radii[l], nss[l]).cpu().numpy(), want), l
+        src = ctr
+
+
 def test_ball_query_radius_is_strict():
     xyz = np.float32([[[0.5, 0, 0], [0.25, 0, 0]]])
     got = ops.ball_query(g(np.zeros((1, 1, 3), np.float32)), g(xyz), 0.5, 2).cpu().numpy()
