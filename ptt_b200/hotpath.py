@@ -119,11 +119,38 @@ class HotPath:
                 self.hp.stage_events.setdefault(self.name, []).append((self.start, end))
             return False
 
+    # The kNN table of a transformer block only depends on the block's xyz, which exists long before its features do
+    # (the centroid block's tokens are the first 128 FPS samples of the search cloud): it is computed on a side stream
+    # as soon as the xyz exist and joined right before the block.
+    def _knn_async(self, xyz):
+        out = torch.empty(xyz.shape[0], xyz.shape[1], self.cfg["knn"], dtype=torch.int32, device=xyz.device)
+        if not self.overlap:
+            ops.knn(xyz, self.cfg["knn"], out=out)
+            return out, None
+        if getattr(self, "_aux", None) is None:
+            self._aux = torch.cuda.Stream(self.device)
+        cur = torch.cuda.current_stream()
+        self._aux.wait_stream(cur)
+        with torch.cuda.stream(self._aux):
+            ops.knn(xyz, self.cfg["knn"], out=out)
+            ev = self._aux.record_event()
+        return out, ev
+
+    @staticmethod
+    def _join(handle):
+        knn, ev = handle
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        return knn
+
     # a6: one set-abstraction layer (pointnet2_modules.py:57-90), point-major in / out
-    def _sa_layer(self, packed, xyz, feats_pm, npoint, radius, nsample, method, want_cm=False, tag="sa", pre=None):
+    def _sa_layer(self, packed, xyz, feats_pm, npoint, radius, nsample, method, want_cm=False, tag="sa", pre=None,
+                  knn_of_centres=False):
         """pre = (inds, new_xyz, idx): sampling and ball query already done (backbone_branch answers the queries of all
-        three layers with one launch right after the FPS)."""
+        three layers with one launch right after the FPS).  knn_of_centres: also start the kNN table of the centres (the
+        tokens of the transformer block that follows) as soon as they exist; returned as a 5th value."""
         c = self.cfg
+        handle = None
         if pre is not None:
             inds, new_xyz, idx = pre
         else:
@@ -135,19 +162,24 @@ class HotPath:
                 new_xyz = xyz[:, :npoint].contiguous()
             else:
                 raise NotImplementedError(method)
+            if knn_of_centres:
+                handle = self._knn_async(new_xyz)
             with self._Stage(self, tag + ".ball_query"):
                 idx = ops.ball_query(new_xyz, xyz, radius, nsample)
         ws = self._workspace(tag, packed.workspace_bytes(xyz.shape[0], xyz.shape[1], npoint, nsample))
         with self._Stage(self, tag + ".mlp"):
             out_pm, out_cm = ops.sa_mlp_fwd(packed, xyz, feats_pm, new_xyz, idx, radius, c["normalize_xyz"],
                                             want_pm=True, want_cm=want_cm, workspace=ws)
+        if knn_of_centres:
+            return new_xyz, out_pm, out_cm, inds, handle
         return new_xyz, out_pm, out_cm, inds
 
     # a8: PointNet2BackboneLight.branch_forward (pointnet2_backbone.py:41-50)
-    def backbone_branch(self, pts, npoints, tag="search"):
+    def backbone_branch(self, pts, npoints, tag="search", knn_of_seeds=False):
         c = self.cfg
         xyz, feats = pts, None
         inds = []
+        handle = None
         methods = c["sample_methods"]
         pre = [None, None, None]
         if methods[0] == "fps" and all(m in ("sequence", "rs") for m in methods[1:]) and \
@@ -162,6 +194,8 @@ class HotPath:
             for l in range(3):
                 ctr = samples if l == 0 else samples[:, :npoints[l]].contiguous()
                 pre[l] = (inds0 if l == 0 else None, ctr, idxs[l])
+            if knn_of_seeds:
+                handle = self._knn_async(pre[2][1])
         for l in range(3):
             xyz, feats, _, i = self._sa_layer(self.sa[l], xyz, feats, npoints[l], c["radii"][l], c["nsamples"][l],
                                               methods[l], tag="%s.sa%d" % (tag, l + 1), pre=pre[l])
@@ -180,6 +214,8 @@ class HotPath:
         if composed is None:
             composed = torch.arange(n3, device=pts.device).repeat(B, 1)
         composed = composed[:, :n3].contiguous()
+        if knn_of_seeds:
+            return xyz, feat_pm, composed, handle if handle is not None else self._knn_async(xyz)
         return xyz, feat_pm, composed
 
     def forward(self, search, template):
@@ -195,11 +231,11 @@ class HotPath:
             t_xyz, t_feat_pm, t_inds = self.backbone_branch(template, c["npoints_template"], "template")
             t_feat = ops.pm_to_cm(t_feat_pm)
         with torch.cuda.stream(s1):
-            s_xyz, s_feat_pm, s_inds = self.backbone_branch(search, c["npoints_search"])
+            s_xyz, s_feat_pm, s_inds, s_knn = self.backbone_branch(search, c["npoints_search"], knn_of_seeds=True)
             s_feat = ops.pm_to_cm(s_feat_pm)
             ws = self._workspace("centroid.transformer", self.centroid_tr.workspace_bytes(s_xyz.shape[0], s_xyz.shape[1]))
             with self._Stage(self, "centroid.transformer"):
-                cen = ops.transformer_block_fwd(self.centroid_tr, s_xyz, s_feat_pm, workspace=ws)
+                cen = ops.transformer_block_fwd(self.centroid_tr, s_xyz, s_feat_pm, knn_idx=self._join(s_knn), workspace=ws)
             # glue: [score | feats], rows padded to a multiple of 4 floats so that the per-point layer-1 contraction of
             # the box SA reads 16-byte aligned rows (tensor-core path); the padding columns are never read (C = 257)
             C = cen.shape[2] + 1
@@ -208,11 +244,12 @@ class HotPath:
             votes_pm[:, :, 1:C] = cen
             if votes_pm.shape[2] > C:
                 votes_pm[:, :, C:] = 0.0
-            b_xyz, b_feat_pm, b_feat, _ = self._sa_layer(self.box_sa, s_xyz, votes_pm, c["box_npoint"], c["box_radius"],
-                                                         c["box_nsample"], "fps", want_cm=True, tag="box.sa")
+            b_xyz, b_feat_pm, b_feat, _, b_knn = self._sa_layer(self.box_sa, s_xyz, votes_pm, c["box_npoint"], c["box_radius"],
+                                                                c["box_nsample"], "fps", want_cm=True, tag="box.sa",
+                                                                knn_of_centres=True)
             ws = self._workspace("box.transformer", self.box_tr.workspace_bytes(b_xyz.shape[0], b_xyz.shape[1]))
             with self._Stage(self, "box.transformer"):
-                box = ops.transformer_block_fwd(self.box_tr, b_xyz, b_feat_pm, workspace=ws)
+                box = ops.transformer_block_fwd(self.box_tr, b_xyz, b_feat_pm, knn_idx=self._join(b_knn), workspace=ws)
         cur.wait_stream(s1)
         cur.wait_stream(s2)
         if not torch.cuda.is_current_stream_capturing():
@@ -244,7 +281,7 @@ class HotPath:
             t_xyz, t_feat_pm, t_inds = self.backbone_branch(template, c["npoints_template"], "template")
             t_feat = ops.pm_to_cm(t_feat_pm)
         with torch.cuda.stream(s1):
-            s_xyz, s_feat_pm, s_inds = self.backbone_branch(search, c["npoints_search"])
+            s_xyz, s_feat_pm, s_inds, s_knn = self.backbone_branch(search, c["npoints_search"], knn_of_seeds=True)
             s_feat = ops.pm_to_cm(s_feat_pm)
             s1.wait_stream(s2)
             B, n, _ = s_xyz.shape
@@ -255,7 +292,7 @@ class HotPath:
             # ---- centroid head
             ws = self._workspace("centroid.transformer", self.centroid_tr.workspace_bytes(B, n))
             with self._Stage(self, "centroid.transformer"):
-                cen = ops.transformer_block_fwd(self.centroid_tr, s_xyz, cos_pm, workspace=ws)
+                cen = ops.transformer_block_fwd(self.centroid_tr, s_xyz, cos_pm, knn_idx=self._join(s_knn), workspace=ws)
             with self._Stage(self, "centroid.heads"):
                 d = cen.shape[2]
                 cls = self.cla(cen.reshape(B * n, d)).reshape(B, n)                           # :87
@@ -269,11 +306,11 @@ class HotPath:
                 vf[:, :, 0] = torch.sigmoid(cls)
                 vf[:, :, 1:1 + d] = res[:, :, 3:]
             # ---- box head
-            b_xyz, b_feat_pm, _, _ = self._sa_layer(self.box_sa, votes, vf, c["box_npoint"], c["box_radius"],
-                                                    c["box_nsample"], "fps", tag="box.sa")
+            b_xyz, b_feat_pm, _, _, b_knn = self._sa_layer(self.box_sa, votes, vf, c["box_npoint"], c["box_radius"],
+                                                           c["box_nsample"], "fps", tag="box.sa", knn_of_centres=True)
             ws = self._workspace("box.transformer", self.box_tr.workspace_bytes(B, b_xyz.shape[1]))
             with self._Stage(self, "box.transformer"):
-                box = ops.transformer_block_fwd(self.box_tr, b_xyz, b_feat_pm, workspace=ws)
+                box = ops.transformer_block_fwd(self.box_tr, b_xyz, b_feat_pm, knn_idx=self._join(b_knn), workspace=ws)
             with self._Stage(self, "box.heads"):
                 m = b_xyz.shape[1]
                 est = self.refine(box.reshape(B * m, box.shape[2])).reshape(B, m, -1)           # :88

@@ -266,11 +266,14 @@ def pm_to_cm(src, C=None):
     return dst
 
 
-def knn(xyz, k):
+def knn(xyz, k, out=None):
     _req(xyz, _F, 3, "xyz")
     B, n, _ = xyz.shape
     with _DeviceGuard(xyz.device):
-        out = torch.empty(B, n, int(k), dtype=_I, device=xyz.device)
+        if out is None:
+            out = torch.empty(B, n, int(k), dtype=_I, device=xyz.device)
+        elif tuple(_req(out, _I, 3, "out").shape) != (B, n, int(k)):
+            raise PttError("knn: out must be (B,n,k) int32")
         check(_lib.lib().ptt_knn(_ptr(xyz), B, n, int(k), _ptr(out), _stream()), "ptt_knn")
     return out
 
