@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-whole-model", action="store_true", help="skip the whole-tracker-forward figure")
+    ap.add_argument("--no-tracking", action="store_true", help="skip the batched tracking-loop figure (SURVEY 8(f) N3)")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-modules-on-this-GPU figure")
     ap.add_argument("--sustain-s", type=float, default=2.5, help="length of the sustained region in seconds (0 = skip)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
@@ -226,6 +227,7 @@ def run_reference(a):
 
 
 def run_b200(a):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -438,6 +440,56 @@ def run_b200(a):
                                "inputs resident in HBM, eager launches as the reference issues them"}
             del ref
 
+    # ---- the tracking loop itself.  T independent synthetic tracklets advance in lockstep; per frame the
+    # raw clouds (pinned host) are copied H2D, cropped around the previous boxes, resampled, run through the whole tracker
+    # forward and the boxes updated -- all inside one CUDA graph (ptt_b200.tracking.BatchedTracker).  "tracked frames/s" =
+    # T * frames / wall time incl. the H2D copies.  The reference's loop is T = 1 with numpy pre / post-processing on the
+    # host and a host round trip per frame: `host_prepost_b1` times that structure with OUR model at batch 1 (the oracle's
+    # numpy restatement of the reference's crop / regularize / box update as the host part -- a baseline leg).
+    track = None
+    if not a.no_tracking and scaled_cfg(a) is None:
+        from ptt_b200 import synth_tracks, tracking
+        track = {}
+        n_frames, cap = 17, 5200
+        sd_full = synth.full_model_state_dict(0)
+        for T in (1, 8, 64):
+            tracks = synth_tracks.make_tracklets(T, n_frames, seed=40 + rank, points_per_frame=4200)
+            frames = [tuple(torch.from_numpy(x).pin_memory() for x in synth_tracks.pad_frames(tracks, i, cap)) for i in range(n_frames)]
+            first = torch.from_numpy(np.stack([b[0].as_row() for _, b in tracks]))
+            trk = tracking.BatchedTracker(sd_full, T, cap, n_frames, device=dev)
+            trk.reset(frames[0][0], frames[0][1], first)
+            tracking.run_tracklets(trk, frames[1:5])              # warm-up incl. graph capture
+            trk.reset(frames[0][0], frames[0][1], first)
+            barrier()
+            t0 = time.perf_counter()
+            res = tracking.run_tracklets(trk, frames[1:])
+            dt = time.perf_counter() - t0
+            assert bool(torch.isfinite(res).all())
+            track["T=%d" % T] = {"tracked_frames_per_s": T * (n_frames - 1) / dt, "ms_per_frame_step": dt * 1e3 / (n_frames - 1),
+                                 "h2d_bytes_per_frame_step": frames[1][0].numel() * 4 + frames[1][1].numel() * 4}
+            if T == 1 and world == 1 and not a.no_cpu_baseline:
+                from oracle import tracking_ref
+                hp1 = hotpath.HotPath(sd_full, device=dev)
+                clouds, boxes = tracks[0]
+
+                def model(sr, tm):
+                    o = hp1.forward_host(torch.from_numpy(sr).pin_memory(), torch.from_numpy(tm).pin_memory(),
+                                         outputs=("pred_box_data",), full=True)
+                    return o["pred_box_data"][0].numpy()
+                tracking_ref.track(clouds[:4], boxes[0], model)
+                t0 = time.perf_counter()
+                tracking_ref.track(clouds, boxes[0], model)
+                dt1 = time.perf_counter() - t0
+                track["host_prepost_b1"] = {"tracked_frames_per_s": (n_frames - 1) / dt1, "ms_per_frame": dt1 * 1e3 / (n_frames - 1),
+                                            "what": "the reference's loop structure: numpy crop / regularize / box update on the "
+                                                    "host per frame (oracle/tracking_ref.py), HotPath.forward_host(full=True) at "
+                                                    "batch 1 with a host round trip per frame"}
+                del hp1
+            del trk
+        track["what"] = ("BatchedTracker: %d frames per tracklet, ~4200 raw points per frame (padded to %d), crop + resample + "
+                         "whole tracker forward + box update in one CUDA graph per frame, H2D of the raw clouds staged one frame "
+                         "ahead; wall clock" % (n_frames - 1, cap))
+
     dev_ms, e2e_ms, wall_ms, pipe_ms, e2e_all_ms = shard.max_over_ranks([dev_ms, e2e_s * 1e3, t_wall * 1e3, pipe_ms, e2e_all_s * 1e3],
                                                                         device=dev)   # slowest rank
 
@@ -515,6 +567,8 @@ def run_b200(a):
                                  "how": "same depth-2 pipeline of graph replays as `value`, back to back for >= %.1f s" % a.sustain_s}
         if ref_gpu is not None:
             line["reference_modules_gpu"] = ref_gpu
+        if track is not None:
+            line["tracking"] = track
         if whole is not None:
             line["whole_model"] = {"value": shard.whole_job_throughput(B * a.steps, n_gpus, whole[0] * 1e-3), "unit": UNIT,
                                    "ms_per_step": whole[0] / a.steps, "extra_stage_ms": whole[1],

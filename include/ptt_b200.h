@@ -248,6 +248,34 @@ PTT_API int ptt_transformer_std_fwd(const float* xyz, const float* features, int
                             const float* params, float* out, float* attn_or_null, void* workspace,
                             size_t workspace_bytes, ptt_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * N3  The per-frame pre / post-processing of the tracking loop, for T independent tracklets at once
+ *     (tools/eval_utils/eval_tracking_utils.py:140-274; ptt/datasets/kitti/kitti_tracking_utils.py:192-367).
+ *     Box state of a tracklet = 15 doubles: center(3) | rotation matrix row-major(9) | wlh(3).  Clouds are padded
+ *     batches (T,cap,3) float32 with per-tracklet counts.  Arithmetic as restated in oracle/tracking_ref.py.
+ * ------------------------------------------------------------------------------------------- */
+/* np.random.seed(seed): the first n 32-bit outputs of MT19937 (init_genrand seeding) into HOST memory h_out. */
+PTT_API int ptt_mt19937_stream(unsigned seed, int n, unsigned* h_out);
+/* crop_center_pc / get_model (kitti_tracking_utils.py:219-237,300-340): every source s (1 or 2; h_* are HOST arrays of
+ * n_sources DEVICE pointers / ints) is cropped around its box -- world-frame AABB of the 4*scale box +- 2*offset, then
+ * box-frame AABB of the scale box +- margin (search != 0: offset + 0.6*wlh[1], the search area :323; else offset, the
+ * template :333) -- and written in the box frame, order preserved, sources concatenated: out (T,cap_out,3),
+ * out_counts (T).  h_precropped[s] != 0: source s is copied as it is (an already cropped part of the template). */
+PTT_API int ptt_track_crop(int T, int n_sources, const float* const* h_points, const int* const* h_counts,
+                   const double* const* h_boxes, const int* h_caps, const int* h_precropped, double offset, double scale,
+                   int search, float* out, int cap_out, int* out_counts, ptt_stream_t stream);
+/* regularize_pc(istrain=False) (:342-367): n = counts[t] points -> size points: zeros when n <= 2, a copy when
+ * n == size, else np.random.seed(1); points[np.random.randint(0, n, size)].  mt_stream = ptt_mt19937_stream(1, ...)
+ * in DEVICE memory (mt_len >= 4*size); mt_pos (T) receives the stream position after a resampling (unchanged otherwise). */
+PTT_API int ptt_track_regularize(const float* points, const int* counts, int T, int cap, int size, const unsigned* mt_stream,
+                         int mt_len, int* mt_pos, float* out, ptt_stream_t stream);
+/* post_process (eval_tracking_utils.py:266-274) after the on-device proposal selection: get_box_by_offset (:192-216) of
+ * best_box (T,ld_best) = (x, y, z, theta_degrees, ...) float32 applied to box_state (T,15) in place (its two
+ * np.random.uniform(-1,1) clamps consume mt_stream at mt_pos); the new state is also stored at
+ * results[*frame_idx] ((max_frames,T,15)) and *frame_idx is incremented. */
+PTT_API int ptt_track_update(const float* best_box, int ld_best, double* box_state, int T, int use_z, const unsigned* mt_stream,
+                     int mt_len, int* mt_pos, double* results, int max_frames, int* frame_idx, ptt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

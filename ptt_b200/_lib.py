@@ -62,6 +62,10 @@ SIGNATURES = {
     "ptt_transformer_std_pack_params": (c_int, [c_int, c_int] + [_P] * 11 + [_P, _P]),
     "ptt_transformer_std_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "ptt_transformer_std_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "ptt_mt19937_stream": (c_int, [ctypes.c_uint, c_int, _P]),
+    "ptt_track_crop": (c_int, [c_int, c_int, _PP, _PP, _PP, _IP, _IP, ctypes.c_double, ctypes.c_double, c_int, _P, c_int, _P, _P]),
+    "ptt_track_regularize": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P]),
+    "ptt_track_update": (c_int, [_P, c_int, _P, c_int, c_int, _P, c_int, _P, _P, c_int, _P, _P]),
 }
 
 # include/ptt_b200_tuning.h: process-wide test / tuning switches.  Bound for tests/ and tools/ only -- nothing under

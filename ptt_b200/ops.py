@@ -616,3 +616,69 @@ def transformer_std_fwd(packed, xyz, features, want_attn=True, workspace=None):
         check(L.ptt_transformer_std_fwd(_ptr(xyz), _ptr(features), B, n, packed.d_points, packed.d_model, _ptr(packed.params),
                                         _ptr(out), _ptr(attn), _ptr(ws), ws.numel() * 4, _stream()), "ptt_transformer_std_fwd")
     return (out, attn) if want_attn else out
+
+
+# ------------------------------------------------------------------------------------------------
+# N3: per-frame pre / post-processing of the tracking loop (csrc/tracking.cu)
+# ------------------------------------------------------------------------------------------------
+_F64 = torch.float64
+
+
+def mt19937_stream(n, seed=1, device=None):
+    """First n 32-bit outputs of MT19937 seeded like np.random.seed(seed), as an int32-typed (bit pattern) tensor."""
+    host = torch.empty(int(n), dtype=_I)
+    check(_lib.lib().ptt_mt19937_stream(int(seed), int(n), ctypes.c_void_p(host.data_ptr())), "ptt_mt19937_stream")
+    return host.to(device) if device is not None else host
+
+
+def track_crop(sources, offset, scale, search, out, out_counts):
+    """sources: 1 or 2 tuples (points (T,cap,3) f32, counts (T) i32, boxes (T,15) f64 | None = precropped) -> out
+    (T,cap_out,3), out_counts (T) filled in place (ptt_track_crop)."""
+    n = len(sources)
+    if not 1 <= n <= 2:
+        raise PttError("track_crop: 1 or 2 sources")
+    T = out.shape[0]
+    _req(out, _F, 3, "out"), _req(out_counts, _I, 1, "out_counts")
+    need = 0
+    for pts, cnt, box in sources:
+        _req(pts, _F, 3, "points"), _req(cnt, _I, 1, "counts")
+        if box is not None:
+            _req(box, _F64, 2, "boxes")
+            if tuple(box.shape) != (T, 15):
+                raise PttError("track_crop: boxes must be (T,15) float64")
+        if pts.shape[0] != T or pts.shape[2] != 3 or cnt.shape[0] != T:
+            raise PttError("track_crop: points (T,cap,3), counts (T)")
+        need += pts.shape[1]
+    if out.shape[1] < need or out.shape[2] != 3 or out_counts.shape[0] != T:
+        raise PttError("track_crop: out must hold the capacities of all sources (%d rows)" % need)
+    arr = lambda xs: (ctypes.c_void_p * n)(*[x.data_ptr() if x is not None else None for x in xs])
+    with _DeviceGuard(out.device):
+        check(_lib.lib().ptt_track_crop(T, n, arr([s[0] for s in sources]), arr([s[1] for s in sources]),
+                                        arr([s[2] for s in sources]), (ctypes.c_int * n)(*[s[0].shape[1] for s in sources]),
+                                        (ctypes.c_int * n)(*[int(s[2] is None) for s in sources]), float(offset), float(scale),
+                                        int(bool(search)), _ptr(out), out.shape[1], _ptr(out_counts), _stream()), "ptt_track_crop")
+
+
+def track_regularize(points, counts, size, mt, mt_pos, out):
+    """points (T,cap,3), counts (T) -> out (T,size,3) (ptt_track_regularize); mt_pos (T) i32 updated in place."""
+    _req(points, _F, 3, "points"), _req(counts, _I, 1, "counts"), _req(mt, _I, 1, "mt"), _req(mt_pos, _I, 1, "mt_pos")
+    _req(out, _F, 3, "out")
+    T, cap, _ = points.shape
+    if tuple(out.shape) != (T, int(size), 3):
+        raise PttError("track_regularize: out must be (T,size,3)")
+    with _DeviceGuard(points.device):
+        check(_lib.lib().ptt_track_regularize(_ptr(points), _ptr(counts), T, cap, int(size), _ptr(mt), mt.numel(), _ptr(mt_pos),
+                                              _ptr(out), _stream()), "ptt_track_regularize")
+
+
+def track_update(best_box, state, use_z, mt, mt_pos, results, frame_idx):
+    """best_box (T,>=4) f32, state (T,15) f64 in place, results (F,T,15) f64, frame_idx (1,) i32 (ptt_track_update)."""
+    _req(best_box, _F, 2, "best_box"), _req(state, _F64, 2, "state"), _req(results, _F64, 3, "results")
+    _req(frame_idx, _I, 1, "frame_idx"), _req(mt, _I, 1, "mt"), _req(mt_pos, _I, 1, "mt_pos")
+    T = state.shape[0]
+    if best_box.shape[0] != T or best_box.shape[1] < 4 or state.shape[1] != 15 or tuple(results.shape[1:]) != (T, 15):
+        raise PttError("track_update: inconsistent shapes")
+    with _DeviceGuard(state.device):
+        check(_lib.lib().ptt_track_update(_ptr(best_box), best_box.shape[1], _ptr(state), T, int(bool(use_z)), _ptr(mt),
+                                          mt.numel(), _ptr(mt_pos), _ptr(results), results.shape[0], _ptr(frame_idx), _stream()),
+              "ptt_track_update")
