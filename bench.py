@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-whole-model", action="store_true", help="skip the whole-tracker-forward figure")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the training-step figure (BASELINE configs[3])")
     ap.add_argument("--no-tracking", action="store_true", help="skip the batched tracking-loop figure (SURVEY 8(f) N3)")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-modules-on-this-GPU figure")
     ap.add_argument("--sustain-s", type=float, default=2.5, help="length of the sustained region in seconds (0 = skip)")
@@ -490,6 +491,17 @@ def run_b200(a):
                          "whole tracker forward + box update in one CUDA graph per frame, H2D of the raw clouds staged one frame "
                          "ahead; wall clock" % (n_frames - 1, cap))
 
+    # ---- BASELINE configs[3] / SURVEY.md 8(e): the training step with the DDP gradient all-reduce -- the one collective the
+    # path has.  Every rank runs it (so the driver's 1/2/4/8-GPU scaling run records the NCCL all-reduce), max over ranks.
+    train = None
+    if not a.no_train_step and scaled_cfg(a) is None:
+        from ptt_b200 import train as train_mod
+        pipe = None
+        torch.cuda.empty_cache()
+        train = train_mod.time_train_step(dev, world, rank, local_rank, batch=B, steps=max(3, min(a.steps, 5)), warmup=3,
+                                          n_search=a.nsearch, n_template=a.ntemplate)
+        train["ms_per_step"] = shard.max_over_ranks([train["ms_per_step"]], device=dev)[0]
+
     dev_ms, e2e_ms, wall_ms, pipe_ms, e2e_all_ms = shard.max_over_ranks([dev_ms, e2e_s * 1e3, t_wall * 1e3, pipe_ms, e2e_all_s * 1e3],
                                                                         device=dev)   # slowest rank
 
@@ -569,6 +581,14 @@ def run_b200(a):
             line["reference_modules_gpu"] = ref_gpu
         if track is not None:
             line["tracking"] = track
+        if train is not None:
+            line["train_step"] = {"value": shard.whole_job_throughput(B, n_gpus, train["ms_per_step"] * 1e-3), "unit": UNIT,
+                                  **train, "n_gpus": n_gpus, "scaling": "weak",
+                                  "collective": ("NCCL gradient all-reduce (DistributedDataParallel), %d bytes per step"
+                                                 % train["allreduce_bytes_per_step"]) if n_gpus > 1 else "none (1 GPU)",
+                                  "what": "forward in train() mode (BatchNorm batch statistics) + L2 loss + backward + DDP gradient "
+                                          "all-reduce + clip_grad_norm_(10) + Adam, as train_utils.py:40-51 / ptt.yaml OPTIMIZATION; "
+                                          "CUDA events, max over ranks"}
         if whole is not None:
             line["whole_model"] = {"value": shard.whole_job_throughput(B * a.steps, n_gpus, whole[0] * 1e-3), "unit": UNIT,
                                    "ms_per_step": whole[0] / a.steps, "extra_stage_ms": whole[1],

@@ -249,6 +249,44 @@ PTT_API int ptt_transformer_std_fwd(const float* xyz, const float* features, int
                             size_t workspace_bytes, ptt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training path (BASELINE configs[3]): BatchNorm on batch statistics and gradients.
+ *     Activations are pair-row matrices (rows, ld) with ld % 4 == 0 and 16-byte aligned bases.  A layer's normalised
+ *     output is never stored: consumers apply relu(ka[c] * y + kb[c]) while loading the PRE-BatchNorm output y.
+ *     Reference: Conv2d 1x1 -> BatchNorm2d -> ReLU of pytorch_utils.py:12-36 in train() mode, F.max_pool2d of
+ *     pointnet2_modules.py:85, and torch autograd of both; nn.Linear of transformer_block/variants.py.
+ * ------------------------------------------------------------------------------------------- */
+/* ptt_linear_fwd with the A operand transformed on load: x <- relu(a_ka[k] * x + a_kb[k]) (both NULL: plain). */
+PTT_API int ptt_linear_fwd_ex(const float* x, int ldx, int R, int K, const float* a_ka, const float* a_kb, const float* params,
+                      int Cout, int relu, const float* residual, int ldr, float* y, int ldy, ptt_stream_t stream);
+/* Weight gradient: dw (M,ldw)[:, 0:N] += dy (R,ldy)[:, 0:M]^T . f(x (R,ldx)[:, 0:N]), f = identity or relu(ka*x + kb)
+ * per column of x; tcgen05 with MN-major operands, split over the rows, fp32 atomics into dw (zero it first). */
+PTT_API int ptt_linear_wgrad(const float* dy, int ldy, const float* x, int ldx, const float* x_ka, const float* x_kb,
+                     long long R, int M, int N, float* dw, int ldw, ptt_stream_t stream);
+/* sums (2,C) double <- column sums of y and y*y over R rows (phase 1 of the two-phase BatchNorm). */
+PTT_API int ptt_col_stats(const float* y, int ldy, long long R, int C, double* sums, ptt_stream_t stream);
+/* Phase 2: mean / biased variance from sums -> ka = gamma*rstd, kb = beta - mean*ka, mean, rstd (C floats each);
+ * running_mean / running_var (may be NULL) updated as torch does (momentum, unbiased variance). */
+PTT_API int ptt_bn_train_finalize(const double* sums, long long R, int C, const float* gamma, const float* beta, float eps,
+                          float momentum, float* running_mean, float* running_var, float* ka, float* kb, float* mean,
+                          float* rstd, ptt_stream_t stream);
+/* QueryAndGroup as a pair-row matrix in the reference's channel order (pointnet2_utils.py:350-361):
+ * rows_out[(b,j,s), :] = [ (xyz[idx]-new_xyz[j]) (/radius) | feats[idx, 0:C] | 0 ], feats point-major (B,N,ldf). */
+PTT_API int ptt_sa_group_rows(const float* xyz, const float* feats, int ldf, const float* new_xyz, const int* idx, int B, int N,
+                      int M, int ns, int C, float radius, int normalize_xyz, float* rows_out, int ld, ptt_stream_t stream);
+/* Its backward: scatter-add (atomics, like _ext.group_points_grad) of d_rows into d_feats (B,N,ldf) and, when not
+ * NULL, d_xyz (B,N,3) / d_new_xyz (B,M,3).  The outputs are accumulated into (zero them first). */
+PTT_API int ptt_sa_group_rows_grad(const float* d_rows, int ld, const int* idx, int B, int N, int M, int ns, int C, float radius,
+                           int normalize_xyz, float* d_feats, int ldf, float* d_xyz, float* d_new_xyz, ptt_stream_t stream);
+/* out (groups,ldo) = max over the ns rows of each group of relu(ka*y + kb); argmax (groups,C) int32 = first maximum. */
+PTT_API int ptt_bn_relu_maxpool(const float* y, int ldy, long long groups, int ns, int C, const float* ka, const float* kb,
+                        float* out, int ldo, int* argmax, ptt_stream_t stream);
+/* Backward of y -> relu(BatchNorm_train(y)) [-> max over ns when argmax is given, dz then (R/ns, ldz)]:
+ * dy (R,ld_dy) = gamma*rstd*(m - s1/R - yhat*s2/R), m = dz*[ka*y+kb > 0]; sums (2,C) double <- (s1 = d beta, s2 = d gamma). */
+PTT_API int ptt_bn_relu_bwd(const float* dz, int ldz, const int* argmax_or_null, int ns, const float* y, int ldy, long long R,
+                    int C, const float* ka, const float* kb, const float* mean, const float* rstd, const float* gamma,
+                    double* sums, float* dy, int ld_dy, ptt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * N3  The per-frame pre / post-processing of the tracking loop, for T independent tracklets at once
  *     (tools/eval_utils/eval_tracking_utils.py:140-274; ptt/datasets/kitti/kitti_tracking_utils.py:192-367).
  *     Box state of a tracklet = 15 doubles: center(3) | rotation matrix row-major(9) | wlh(3).  Clouds are padded

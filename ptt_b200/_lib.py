@@ -62,6 +62,14 @@ SIGNATURES = {
     "ptt_transformer_std_pack_params": (c_int, [c_int, c_int] + [_P] * 11 + [_P, _P]),
     "ptt_transformer_std_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "ptt_transformer_std_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "ptt_linear_fwd_ex": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_int, _P, c_int, _P]),
+    "ptt_linear_wgrad": (c_int, [_P, c_int, _P, c_int, _P, _P, ctypes.c_longlong, c_int, c_int, _P, c_int, _P]),
+    "ptt_col_stats": (c_int, [_P, c_int, ctypes.c_longlong, c_int, _P, _P]),
+    "ptt_bn_train_finalize": (c_int, [_P, ctypes.c_longlong, c_int, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "ptt_sa_group_rows": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_int, _P]),
+    "ptt_sa_group_rows_grad": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_int, _P, _P, _P]),
+    "ptt_bn_relu_maxpool": (c_int, [_P, c_int, ctypes.c_longlong, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
+    "ptt_bn_relu_bwd": (c_int, [_P, c_int, _P, c_int, _P, c_int, ctypes.c_longlong, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "ptt_mt19937_stream": (c_int, [ctypes.c_uint, c_int, _P]),
     "ptt_track_crop": (c_int, [c_int, c_int, _PP, _PP, _PP, _IP, _IP, ctypes.c_double, ctypes.c_double, c_int, _P, c_int, _P, _P]),
     "ptt_track_regularize": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P]),

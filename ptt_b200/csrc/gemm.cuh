@@ -10,6 +10,10 @@ struct PttGemmArgs {
   const float* x = nullptr;
   int ldx = 0;
   const int* a_rows = nullptr;  // optional: output row r reads x row a_rows[r]
+  // optional per-K-channel affine + ReLU applied to the A operand while it is staged: x <- relu(a_ka[k] * x + a_kb[k]).
+  // The training path feeds a layer with the PRE-BatchNorm output of the previous one this way (tcgen05 path only).
+  const float* a_ka = nullptr;
+  const float* a_kb = nullptr;
   int R = 0, K = 0;
   const float* wt = nullptr;   // fp32 transposed weight (K rows of ldw floats): the CUDA-core path
   int ldw = 0;
@@ -44,6 +48,11 @@ bool ptt_tc_gemm_supported(const PttGemmArgs& a);
 int ptt_tc_gemm_launch(const PttGemmArgs& a, const void* wimg, cudaStream_t st);
 // floats occupied by the tcgen05 image of a (Cout, K) weight
 static inline size_t ptt_tc_weight_floats(int K, int Cout) { return ptt_tc_weight_halves(K, Cout) / 2; }
+
+// Weight gradient (tc_wgrad.cu): dW (M, ldw)[:, 0:N] += dY (R, ldy)[:, 0:M]^T . f(X (R, ldx)[:, 0:N]), f = identity or
+// relu(ka[n] * x + kb[n]); rows are read as float4 (ldy, ldx multiples of 4, 16-byte aligned bases)
+int ptt_tc_wgrad_launch(const float* dy, int ldy, const float* x, int ldx, const float* x_ka, const float* x_kb,
+                        long long R, int M, int N, float* dw, int ldw, cudaStream_t st);
 
 // nn.Linear (Cout,K) weight [+bias] -> transposed image (K+1 rows x ldw, last row = bias), zero padded
 int ptt_linear_pack_launch(const float* weight, const float* bias, int K, int Cout, float* params, cudaStream_t st);

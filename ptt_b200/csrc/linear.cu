@@ -127,7 +127,8 @@ int ptt_gemm_launch(const PttGemmArgs& a, cudaStream_t st) {
     const bool ok = a.wimg != nullptr && ptt_tc_gemm_supported(a) && a.x_bstride % 4 == 0;
     return ok ? ptt_tc_gemm_launch(a, a.wimg, st) : PTT_ERR_UNSUPPORTED;
   }
-  if (a.wimg != nullptr && !g_force_ffma && ptt_tc_gemm_supported(a)) return ptt_tc_gemm_launch(a, a.wimg, st);
+  if (a.wimg != nullptr && (!g_force_ffma || a.a_ka != nullptr) && ptt_tc_gemm_supported(a)) return ptt_tc_gemm_launch(a, a.wimg, st);
+  if (a.a_ka != nullptr) return PTT_ERR_UNSUPPORTED;      // the operand transform exists on the tensor-core path only
   return ptt_gemm_launch_ffma(a, st);
 }
 

@@ -127,10 +127,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         }
       }
     };
+    // optional A transform (training path): x <- relu(ka[k] * x + kb[k]) for the four k columns this thread stages
+    const bool xform = g.a_ka != nullptr;
+    auto affine_relu = [&](int kb, float4 (&v)[8]) {
+      const int k = kb * TBK + c4 * 4;
+      float ka[4], kc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ka[u] = k + u < g.K ? __ldg(g.a_ka + k + u) : 0.f;
+        kc[u] = k + u < g.K ? __ldg(g.a_kb + k + u) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i].x = fmaxf(fmaf(v[i].x, ka[0], kc[0]), 0.f);
+        v[i].y = fmaxf(fmaf(v[i].y, ka[1], kc[1]), 0.f);
+        v[i].z = fmaxf(fmaf(v[i].z, ka[2], kc[2]), 0.f);
+        v[i].w = fmaxf(fmaf(v[i].w, ka[3], kc[3]), 0.f);
+      }
+    };
     float4 cur[8], nxt[8];
     load_block(0, cur);
     for (int kb = 0; kb < KB; ++kb) {
       if (kb + 1 < KB) load_block(kb + 1, nxt);
+      if (xform) affine_relu(kb, cur);
       tc::mbar_wait(&empty[stage], phase ^ 1);
       uint8_t* a_hi = smem + stage * Cfg::STAGE_BYTES;
       uint8_t* a_lo = a_hi + A_HALF_BYTES;

@@ -149,6 +149,12 @@ class PointnetSAModuleVotes(_PackCache, nn.Module):
         if use_xyz and len(mlp_spec) > 0:
             mlp_spec[0] += 3          # in place, like the reference (pointnet2_modules.py:51-53)
         self.mlp_module = _SharedMLP(mlp_spec, bn)
+        self.native_train = True      # train() mode runs the native kernels; False: the reference's decomposition in torch
+
+    def _bn_everywhere(self):
+        # what the native training kernels cover: conv (no bias) + BatchNorm + ReLU layers, widths in float4 granules
+        return all(hasattr(u, "normlayer") and u.conv.bias is None and u.conv.out_channels % 4 == 0 and
+                   u.conv.out_channels <= 1024 for u in self.mlp_module)
 
     def _build_packed(self):
         ws, scales, shifts = [], [], []
@@ -195,10 +201,16 @@ class PointnetSAModuleVotes(_PackCache, nn.Module):
                                              want_pm=False, want_cm=True)
             return new_xyz, new_features, inds.to(torch.int64)
 
-        # the reference's decomposition (pointnet2_modules.py:62-90, pointnet2_utils.py:320-380) under autograd
         xyz_flipped = xyz.transpose(1, 2).contiguous()
         new_xyz = _Gather.apply(xyz_flipped, inds32).transpose(1, 2).contiguous()
         idx = ops.ball_query(new_xyz.detach(), xyz.detach(), self.radius, self.nsample)
+        if self.native_train and self.use_xyz and self.training and self._bn_everywhere():
+            # native training path (ptt_b200/train_ops.py): tcgen05 contractions, two-phase BatchNorm statistics, fused
+            # BatchNorm / ReLU / max-pool backward -- forward AND backward are libptt_b200 kernels
+            from . import train_ops
+            new_features = train_ops.sa_train(xyz, features, new_xyz, idx, self.radius, self.normalize_xyz, self.mlp_module)
+            return new_xyz, new_features, inds.to(torch.int64)
+        # the reference's decomposition (pointnet2_modules.py:62-90, pointnet2_utils.py:320-380) under autograd
         grouped_xyz = _Group.apply(xyz_flipped, idx) - new_xyz.transpose(1, 2).unsqueeze(-1)
         if self.normalize_xyz:
             grouped_xyz = grouped_xyz / self.radius

@@ -281,19 +281,32 @@ def knn(xyz, k, out=None):
 class PackedLinear:
     """nn.Linear parameters in the library's packed layout (ptt_linear_pack)."""
 
-    def __init__(self, weight, bias=None):
+    def __init__(self, weight, bias=None, check_range=True):
         _req(weight, _F, 2, "weight")
         self.cout, self.k = weight.shape
-        check_split_range("linear weight", weight)
+        if check_range:
+            check_split_range("linear weight", weight)
         L = _lib.lib()
         with _DeviceGuard(weight.device):
             self.params = torch.empty(L.ptt_linear_params_floats(self.k, self.cout), dtype=_F, device=weight.device)
-            check(L.ptt_linear_pack(_ptr(weight), _ptr(bias), self.k, self.cout, _ptr(self.params), _stream()),
-                  "ptt_linear_pack")
+        self.repack(weight, bias)
 
-    def __call__(self, x, relu=False, residual=None):
+    def repack(self, weight, bias=None):
+        """Pack new values of the same shape into the existing image (no allocation, no synchronisation, no range check:
+        the training path repacks every step)."""
+        _req(weight, _F, 2, "weight")
+        if tuple(weight.shape) != (self.cout, self.k):
+            raise PttError("repack: weight must be (%d,%d)" % (self.cout, self.k))
+        with _DeviceGuard(weight.device):
+            check(_lib.lib().ptt_linear_pack(_ptr(weight), _ptr(bias), self.k, self.cout, _ptr(self.params), _stream()),
+                  "ptt_linear_pack")
+        return self
+
+    def __call__(self, x, relu=False, residual=None, in_affine=None, ld_out=None):
         """x (R, ldx >= K): the first K columns of every row are the input (rows padded to a multiple of 4 floats take
-        the tensor-core path); residual (R, ldr >= Cout) is added after the activation."""
+        the tensor-core path); residual (R, ldr >= Cout) is added after the activation.  in_affine = (ka, kb): the
+        input is relu(ka[k] * x + kb[k]) applied on load (training path).  ld_out: row stride of the result (>= Cout;
+        the padding columns are left unwritten)."""
         _req(x, _F, 2, "x")
         R, ldx = x.shape
         if ldx < self.k:
@@ -304,11 +317,19 @@ class PackedLinear:
             ldr = residual.shape[1]
             if residual.shape[0] != R or ldr < self.cout:
                 raise PttError("linear: residual must be (R, ld >= Cout)")
+        ldy = self.cout if ld_out is None else int(ld_out)
+        if ldy < self.cout:
+            raise PttError("linear: ld_out < Cout")
+        ka = kb = None
+        if in_affine is not None:
+            ka, kb = in_affine
+            _req(ka, _F, 1, "ka"), _req(kb, _F, 1, "kb")
+            if ka.numel() < self.k or kb.numel() < self.k:
+                raise PttError("linear: in_affine vectors shorter than K")
         with _DeviceGuard(x.device):
-            y = torch.empty(R, self.cout, dtype=_F, device=x.device)
-            check(_lib.lib().ptt_linear_fwd(_ptr(x), ldx, R, self.k, _ptr(self.params), self.cout, int(relu), _ptr(residual),
-                                            ldr, _ptr(y), self.cout, _stream()),
-                  "ptt_linear_fwd")
+            y = torch.empty(R, ldy, dtype=_F, device=x.device) if ldy == self.cout else torch.zeros(R, ldy, dtype=_F, device=x.device)
+            check(_lib.lib().ptt_linear_fwd_ex(_ptr(x), ldx, R, self.k, _ptr(ka), _ptr(kb), _ptr(self.params), self.cout, int(relu),
+                                               _ptr(residual), ldr, _ptr(y), ldy, _stream()), "ptt_linear_fwd_ex")
         return y
 
 

@@ -55,3 +55,48 @@ class HotPathNet(nn.Module):
         b_xyz, b_feat, _ = self.box_voting_head.vote_aggregation(s_xyz, votes_feats, self.box_npoint)
         box, _ = self.box_voting_head.transformer_block(b_xyz, b_feat.transpose(1, 2).contiguous())
         return {"search_feats": s_feat, "template_feats": t_feat, "centroid_feats": cen, "box_sa_feats": b_feat, "box_feats": box}
+
+
+def time_train_step(device, world=1, rank=0, local_rank=0, batch=48, steps=5, warmup=3, n_search=1024, n_template=512):
+    """One training step of the hot path the way the reference trains (tools/train_utils/train_utils.py:40-51,
+    tools/train_tracking.py:158-159, ptt.yaml OPTIMIZATION): forward in train() mode (BatchNorm batch statistics), loss,
+    backward, DistributedDataParallel gradient all-reduce over NCCL (the only collective; needs an initialised process
+    group when world > 1), clip_grad_norm_(10), Adam(lr 1e-3, betas (0.5, 0.999)).  Every rank trains on its own `batch`
+    synthetic frames (weak scaling).  Timed on the device with CUDA events.  Returns a dict (ms_per_step of THIS rank)."""
+    import torch.distributed as dist
+
+    from . import synth
+
+    net = HotPathNet()
+    synth.load_filled(net, seed=0)
+    net = net.to(device).train()
+    model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank]) if world > 1 else net
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.5, 0.999))
+    n_params = sum(p.numel() for p in net.parameters())
+    sets = [(torch.from_numpy(synth.make_clouds(batch, n_search, 3000 + 16 * rank + i, "dense")).to(device),
+             torch.from_numpy(synth.make_clouds(batch, n_template, 4000 + 16 * rank + i, "dense", role="template")).to(device))
+            for i in range(4)]
+
+    def step(i):
+        s, t = sets[i % 4]
+        out = model(s, t)
+        loss = sum((v.float() ** 2).mean() for v in out.values())      # synthetic L2 loss on every block output
+        opt.zero_grad(set_to_none=True)
+        loss.backward()                                                   # DDP all-reduces the gradients in here
+        nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+        opt.step()
+        return loss
+
+    for i in range(warmup):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = [step(i) for i in range(steps)]
+    e1.record()
+    torch.cuda.synchronize(device)
+    return {"ms_per_step": e0.elapsed_time(e1) / steps, "steps": steps, "warmup": warmup, "batch_per_gpu": batch,
+            "parameters": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
+            "loss_first_last": [float(losses[0]), float(losses[-1])]}

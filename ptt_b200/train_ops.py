@@ -1,0 +1,189 @@
+"""Native training path of the hot path's modules: autograd.Functions whose forward AND backward are libptt_b200
+kernels (BASELINE configs[3]; VERDICT r1 "missing" #1).
+
+`sa_train`   one set-abstraction layer in train() mode -- QueryAndGroup -> [Conv2d 1x1 -> BatchNorm2d(batch statistics)
+             -> ReLU] x L -> max over nsample (pointnet2_modules.py:57-90, pytorch_utils.py:12-36) -- with its backward.
+
+Design (csrc/train_ops.cu, tc_gemm.cu, tc_wgrad.cu): activations are pair-row matrices; each layer is one tcgen05
+contraction that writes the PRE-BatchNorm output y_l once; the statistics are a column reduction over y_l; the normalised,
+rectified activation is never stored -- the next contraction (and the weight-gradient contraction in the backward pass)
+apply relu(ka * y + kb) while loading y_l.  Saved for backward: the grouped input rows, y_l per layer, the per-channel
+(ka, kb, mean, rstd) vectors and the max-pool indices.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+from ._lib import check
+from .ops import PttError, _DeviceGuard, _F, _I, _ptr, _req, _stream
+
+_F64 = torch.float64
+
+
+def _pad4(c):
+    return (int(c) + 3) // 4 * 4
+
+
+def linear_wgrad(dy, x, M, N, x_affine=None):
+    """dW (M, N) = dy[:, :M]^T . f(x[:, :N]), f = identity or relu(ka * x + kb) (ptt_linear_wgrad)."""
+    _req(dy, _F, 2, "dy"), _req(x, _F, 2, "x")
+    R = dy.shape[0]
+    if x.shape[0] != R or dy.shape[1] < M or x.shape[1] < N:
+        raise PttError("linear_wgrad: inconsistent shapes")
+    ka, kb = x_affine if x_affine is not None else (None, None)
+    ldw = _pad4(N)
+    with _DeviceGuard(dy.device):
+        dw = torch.zeros(M, ldw, dtype=_F, device=dy.device)
+        check(_lib.lib().ptt_linear_wgrad(_ptr(dy), dy.shape[1], _ptr(x), x.shape[1], _ptr(ka), _ptr(kb), R, int(M), int(N),
+                                          _ptr(dw), ldw, _stream()), "ptt_linear_wgrad")
+    return dw[:, :N]
+
+
+def col_stats(y, C):
+    _req(y, _F, 2, "y")
+    with _DeviceGuard(y.device):
+        sums = torch.empty(2, C, dtype=_F64, device=y.device)
+        check(_lib.lib().ptt_col_stats(_ptr(y), y.shape[1], y.shape[0], int(C), _ptr(sums), _stream()), "ptt_col_stats")
+    return sums
+
+
+def bn_train_finalize(sums, R, gamma, beta, eps, momentum, running_mean, running_var):
+    """-> (ka, kb, mean, rstd); running statistics updated in place."""
+    C = sums.shape[1]
+    with _DeviceGuard(sums.device):
+        vec = torch.empty(4, C, dtype=_F, device=sums.device)
+        check(_lib.lib().ptt_bn_train_finalize(_ptr(sums), int(R), C, _ptr(gamma), _ptr(beta), float(eps), float(momentum),
+                                               _ptr(running_mean), _ptr(running_var), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]),
+                                               _ptr(vec[3]), _stream()), "ptt_bn_train_finalize")
+    return vec[0], vec[1], vec[2], vec[3]
+
+
+def sa_group_rows(xyz, feats_pm, new_xyz, idx, C, radius, normalize):
+    B, N, _ = xyz.shape
+    _, M, ns = idx.shape
+    ld = _pad4(C + 3)
+    with _DeviceGuard(xyz.device):
+        rows = torch.empty(B * M * ns, ld, dtype=_F, device=xyz.device)
+        check(_lib.lib().ptt_sa_group_rows(_ptr(xyz), _ptr(feats_pm), feats_pm.shape[2] if feats_pm is not None else 0,
+                                           _ptr(new_xyz), _ptr(idx), B, N, M, ns, int(C), float(radius), int(bool(normalize)),
+                                           _ptr(rows), ld, _stream()), "ptt_sa_group_rows")
+    return rows
+
+
+def sa_group_rows_grad(d_rows, idx, N, C, radius, normalize, want_feats, want_xyz):
+    B, M, ns = idx.shape
+    with _DeviceGuard(d_rows.device):
+        d_feats = torch.zeros(B, N, _pad4(C), dtype=_F, device=d_rows.device) if want_feats and C > 0 else None
+        d_xyz = torch.zeros(B, N, 3, dtype=_F, device=d_rows.device) if want_xyz else None
+        d_new = torch.zeros(B, M, 3, dtype=_F, device=d_rows.device) if want_xyz else None
+        check(_lib.lib().ptt_sa_group_rows_grad(_ptr(d_rows), d_rows.shape[1], _ptr(idx), B, int(N), M, ns, int(C), float(radius),
+                                                int(bool(normalize)), _ptr(d_feats), d_feats.shape[2] if d_feats is not None else 0,
+                                                _ptr(d_xyz), _ptr(d_new), _stream()), "ptt_sa_group_rows_grad")
+    return d_feats, d_xyz, d_new
+
+
+def bn_relu_maxpool(y, groups, ns, C, ka, kb):
+    with _DeviceGuard(y.device):
+        out = torch.empty(groups, C, dtype=_F, device=y.device)
+        arg = torch.empty(groups, C, dtype=_I, device=y.device)
+        check(_lib.lib().ptt_bn_relu_maxpool(_ptr(y), y.shape[1], int(groups), int(ns), int(C), _ptr(ka), _ptr(kb), _ptr(out), C,
+                                             _ptr(arg), _stream()), "ptt_bn_relu_maxpool")
+    return out, arg
+
+
+def bn_relu_bwd(dz, argmax, ns, y, C, ka, kb, mean, rstd, gamma):
+    """-> (dy (R, C), sums (2, C) float64 = (d beta, d gamma))."""
+    R = y.shape[0]
+    with _DeviceGuard(y.device):
+        dy = torch.empty(R, C, dtype=_F, device=y.device)
+        sums = torch.empty(2, C, dtype=_F64, device=y.device)
+        check(_lib.lib().ptt_bn_relu_bwd(_ptr(dz), dz.shape[1], _ptr(argmax), int(ns), _ptr(y), y.shape[1], R, int(C), _ptr(ka),
+                                         _ptr(kb), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(sums), _ptr(dy), C, _stream()),
+              "ptt_bn_relu_bwd")
+    return dy, sums
+
+
+class _SATrain(torch.autograd.Function):
+    """inputs: xyz (B,N,3), feats_cm (B,C,N) | None, new_xyz (B,M,3), idx (B,M,ns) int32, then per layer
+    (conv weight (Cout,Cin,1,1), bn weight, bn bias, running_mean, running_var)."""
+
+    @staticmethod
+    def forward(ctx, xyz, feats_cm, new_xyz, idx, radius, normalize, eps, momentum, *params):
+        L = len(params) // 5
+        B, N, _ = xyz.shape
+        _, M, ns = idx.shape
+        C = feats_cm.shape[1] if feats_cm is not None else 0
+        feats_pm = ops.cm_to_pm(feats_cm.contiguous(), _pad4(C)) if C else None
+        x0 = sa_group_rows(xyz, feats_pm, new_xyz, idx, C, radius, normalize)
+        R = x0.shape[0]
+        ys, affs, stats = [], [], []
+        src, aff, k_in = x0, None, C + 3
+        for l in range(L):
+            w, g, b, rm, rv = params[5 * l: 5 * l + 5]
+            cout = w.shape[0]
+            lin = ops.PackedLinear(w.detach().reshape(cout, k_in).contiguous(), None, check_range=False)
+            y = lin(src, in_affine=aff)
+            ka, kb, mean, rstd = bn_train_finalize(col_stats(y, cout), R, g.detach(), b.detach(), eps, momentum, rm, rv)
+            ys.append(y)
+            affs.append((ka, kb))
+            stats.append((mean, rstd))
+            src, aff, k_in = y, (ka, kb), cout
+        out, arg = bn_relu_maxpool(ys[-1], B * M, ns, k_in, *affs[-1])
+        ctx.save_for_backward(x0, idx, arg, *ys, *[t for a in affs for t in a], *[t for s in stats for t in s],
+                              *[params[5 * l].detach() for l in range(L)], *[params[5 * l + 1].detach() for l in range(L)])
+        ctx.meta = (L, B, N, M, ns, C, float(radius), bool(normalize))
+        ctx.mark_non_differentiable(arg)
+        return ops.pm_to_cm(out.view(B, M, k_in)), arg
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_arg):
+        L, B, N, M, ns, C, radius, normalize = ctx.meta
+        sv = ctx.saved_tensors
+        x0, idx, arg = sv[0], sv[1], sv[2]
+        ys = sv[3: 3 + L]
+        affs = [(sv[3 + L + 2 * l], sv[3 + L + 2 * l + 1]) for l in range(L)]
+        stats = [(sv[3 + 3 * L + 2 * l], sv[3 + 3 * L + 2 * l + 1]) for l in range(L)]
+        ws = sv[3 + 5 * L: 3 + 6 * L]
+        gs = sv[3 + 6 * L: 3 + 7 * L]
+        grads = [None] * (5 * L)
+        dz = ops.cm_to_pm(grad_out.contiguous())                     # (B, M, C_L) -> pooled rows (B*M, C_L)
+        dz = dz.view(B * M, dz.shape[2])
+        pooled = arg
+        for l in range(L - 1, -1, -1):
+            cout, cin = ws[l].shape[0], ws[l].shape[1]
+            dy, sums = bn_relu_bwd(dz, pooled, ns, ys[l], cout, affs[l][0], affs[l][1], stats[l][0], stats[l][1], gs[l])
+            pooled = None
+            grads[5 * l + 1] = sums[1].float()                       # d gamma
+            grads[5 * l + 2] = sums[0].float()                       # d beta
+            src, aff = (x0, None) if l == 0 else (ys[l - 1], affs[l - 1])
+            grads[5 * l] = linear_wgrad(dy, src, cout, cin, aff).reshape(ws[l].shape)
+            need_dx = l > 0 or ctx.needs_input_grad[0] or (C > 0 and ctx.needs_input_grad[1]) or ctx.needs_input_grad[2]
+            if need_dx:
+                wt = ops.PackedLinear(ws[l].reshape(cout, cin).t().contiguous(), None, check_range=False)
+                dz = wt(dy, ld_out=_pad4(cin))
+        d_xyz = d_feats = d_new = None
+        if ctx.needs_input_grad[0] or (C > 0 and ctx.needs_input_grad[1]) or ctx.needs_input_grad[2]:
+            want_xyz = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
+            d_feats_pm, d_xyz, d_new = sa_group_rows_grad(dz, idx, N, C, radius, normalize, C > 0 and ctx.needs_input_grad[1], want_xyz)
+            if d_feats_pm is not None:
+                d_feats = ops.pm_to_cm(d_feats_pm, C)
+        return (d_xyz, d_feats, d_new, None, None, None, None, None, *grads)
+
+
+def sa_train(xyz, feats_cm, new_xyz, idx, radius, normalize, mlp_module):
+    """The training-mode body of PointnetSAModuleVotes on the native path.  mlp_module: the reference-shaped SharedMLP
+    (layers `layer{i}.conv` / `.normlayer.bn`); its BatchNorm running statistics are updated in place."""
+    params, eps, momentum = [], None, None
+    for unit in mlp_module:
+        if not hasattr(unit, "normlayer") or unit.conv.bias is not None:
+            raise PttError("sa_train: conv (no bias) + BatchNorm layers only (pytorch_utils.py:25-36 with bn=True)")
+        bn = unit.normlayer.bn
+        if eps is None:
+            eps, momentum = bn.eps, (bn.momentum if bn.momentum is not None else 0.1)
+        elif (bn.eps, bn.momentum if bn.momentum is not None else 0.1) != (eps, momentum):
+            raise PttError("sa_train: the BatchNorm layers of one SharedMLP share eps / momentum")
+        params += [unit.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        bn.num_batches_tracked += 1
+    out, _ = _SATrain.apply(xyz, feats_cm, new_xyz, idx, float(radius), bool(normalize), float(eps), float(momentum), *params)
+    return out

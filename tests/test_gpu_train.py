@@ -1,0 +1,140 @@
+"""GPU: the native training path (ptt_b200/train_ops.py; csrc/train_ops.cu, tc_wgrad.cu, tc_gemm.cu's operand transform)
+against torch autograd over the reference's decomposition (fp32, TF32 off): forward values, every gradient, the BatchNorm
+running statistics.  Tolerances: forward 1e-4 (north_star), gradients 1e-3 of the tensor's scale (sums over up to 10^5
+rows in a different order; the weight-gradient atomics are unordered)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import t
+from ptt_b200 import modules, ops, synth, train_ops
+from test_oracle_golden import sa_state_dict
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _true_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def close(a, b, tol, what=""):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    scale = max(float(b.abs().max()), 1e-6)
+    err = float((a - b).abs().max())
+    assert err <= tol * scale, "%s: max |diff| %.3e vs scale %.3e (tol %.1e)" % (what, err, scale, tol)
+
+
+@pytest.mark.parametrize("R,M,N", [(5000, 128, 131), (64, 64, 3), (12345, 256, 259), (4096, 256, 128), (70000, 512, 512),
+                                   (300, 100, 36), (8200, 128, 64)])
+def test_linear_wgrad_vs_torch(R, M, N):
+    rs = np.random.RandomState(R + M)
+    ldy, ldx = (M + 3) // 4 * 4, (N + 3) // 4 * 4
+    dy = torch.from_numpy(rs.standard_normal((R, ldy)).astype(np.float32)).to(DEV)
+    x = torch.from_numpy(rs.standard_normal((R, ldx)).astype(np.float32)).to(DEV)
+    want = dy[:, :M].double().t() @ x[:, :N].double()
+    got = train_ops.linear_wgrad(dy, x, M, N)
+    close(got, want, 2e-5, "plain")
+    ka = torch.from_numpy(rs.uniform(0.5, 1.5, N).astype(np.float32)).to(DEV)
+    kb = torch.from_numpy(rs.normal(0, 0.5, N).astype(np.float32)).to(DEV)
+    want = dy[:, :M].double().t() @ torch.relu(x[:, :N] * ka + kb).double()
+    got = train_ops.linear_wgrad(dy, x, M, N, (ka, kb))
+    close(got, want, 2e-5, "affine + relu on load")
+
+
+def test_linear_fwd_operand_transform_and_padding():
+    rs = np.random.RandomState(3)
+    for R, K, Cout in ((1000, 128, 256), (333, 64, 131), (129, 260, 256)):
+        ld = (K + 3) // 4 * 4
+        x = torch.from_numpy(rs.standard_normal((R, ld)).astype(np.float32)).to(DEV)
+        w = torch.from_numpy((rs.standard_normal((Cout, K)) / np.sqrt(K)).astype(np.float32)).to(DEV)
+        ka = torch.from_numpy(rs.uniform(0.5, 1.5, K).astype(np.float32)).to(DEV)
+        kb = torch.from_numpy(rs.normal(0, 0.5, K).astype(np.float32)).to(DEV)
+        lin = ops.PackedLinear(w)
+        want = torch.relu(x[:, :K] * ka + kb).double() @ w.double().t()
+        got = lin(x, in_affine=(ka, kb), ld_out=(Cout + 3) // 4 * 4)
+        close(got[:, :Cout], want, 2e-5, "fwd_ex %s" % ((R, K, Cout),))
+        w2 = w * 0.5
+        close(lin.repack(w2)(x), x[:, :K].double() @ w2.double().t(), 2e-5, "repack")
+
+
+def test_two_phase_batchnorm_and_pool_vs_torch():
+    rs = np.random.RandomState(5)
+    for groups, ns, C in ((500, 32, 128), (77, 16, 256), (100, 8, 48)):
+        R = groups * ns
+        y = torch.from_numpy(rs.standard_normal((R, C)).astype(np.float32) * 2 + 0.3).to(DEV)
+        gamma = torch.from_numpy(rs.uniform(0.5, 1.5, C).astype(np.float32)).to(DEV)
+        beta = torch.from_numpy(rs.normal(0, 0.3, C).astype(np.float32)).to(DEV)
+        rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        rm2, rv2 = rm.clone(), rv.clone()
+        ka, kb, mean, rstd = train_ops.bn_train_finalize(train_ops.col_stats(y, C), R, gamma, beta, 1e-5, 0.1, rm, rv)
+        yt = y.clone().requires_grad_(True)
+        z = torch.relu(F.batch_norm(yt.t().reshape(1, C, R), rm2, rv2, gamma, beta, training=True, momentum=0.1, eps=1e-5))
+        close(torch.relu(y * ka + kb), z[0].t(), 1e-5, "normalised")
+        close(rm, rm2, 1e-5, "running_mean"), close(rv, rv2, 1e-5, "running_var")
+        pooled, arg = train_ops.bn_relu_maxpool(y, groups, ns, C, ka, kb)
+        zt = z[0].t().reshape(groups, ns, C)
+        close(pooled, zt.max(1)[0], 1e-5, "max pool")
+        # backward through pool + relu + batch norm
+        dout = torch.from_numpy(rs.standard_normal((groups, C)).astype(np.float32)).to(DEV)
+        zt.max(1)[0].backward(dout)
+        dy, sums = train_ops.bn_relu_bwd(dout, arg, ns, y, C, ka, kb, mean, rstd, gamma)
+        close(dy, yt.grad, 1e-4, "dy (pooled)")
+        # dense dz
+        yt.grad = None
+        dz = torch.from_numpy(rs.standard_normal((R, C)).astype(np.float32)).to(DEV)
+        gam = gamma.clone().requires_grad_(True)
+        bet = beta.clone().requires_grad_(True)
+        z2 = torch.relu(F.batch_norm(yt.t().reshape(1, C, R), None, None, gam, bet, training=True, eps=1e-5))
+        z2[0].t().backward(dz)
+        dy, sums = train_ops.bn_relu_bwd(dz, None, 1, y, C, ka, kb, mean, rstd, gamma)
+        close(dy, yt.grad, 1e-4, "dy (dense)")
+        close(sums[1], gam.grad, 1e-4, "d gamma"), close(sums[0], bet.grad, 1e-4, "d beta")
+
+
+SA_TRAIN_CASES = [  # (B, N, C_in, mlp, npoint, radius, ns, xyz requires grad)
+    (4, 512, 128, [128, 128, 128, 256], 256, 0.5, 32, False),        # ptt.yaml SA2
+    (3, 1024, 0, [0, 64, 64, 128], 512, 0.3, 32, False),             # SA1: xyz only
+    (4, 128, 257, [257, 256, 256, 256], 64, 0.3, 16, True),          # the box head's vote aggregation (xyz = votes: grad)
+    (2, 100, 16, [16, 32, 48], 40, 0.6, 8, True),
+]
+
+
+@pytest.mark.parametrize("case", SA_TRAIN_CASES)
+def test_sa_module_native_training_vs_torch_decomposition(case):
+    B, N, cin, mlp, npoint, radius, ns, xyz_grad = case
+    sd = {k: t(v) for k, v in synth.fill_state_dict(sa_state_dict(mlp), seed=500 + N).items()}
+    xyz = torch.from_numpy(synth.make_clouds(B, N, 600 + N, "dense", role="template" if N <= 512 else "search")).to(DEV)
+    feats = torch.from_numpy(synth.features((B, cin, N), seed=601 + N)).to(DEV) if cin else None
+    outs = []
+    for native in (True, False):
+        mod = modules.PointnetSAModuleVotes(mlp=list(mlp), radius=radius, nsample=ns, normalize_xyz=True, sample_method="fps")
+        mod.load_state_dict(sd)
+        mod = mod.to(DEV).train()
+        mod.native_train = native
+        x = xyz.clone().requires_grad_(xyz_grad)
+        f = feats.clone().requires_grad_(True) if cin else None
+        new_xyz, new_feats, inds = mod(x, f, npoint)
+        w = torch.from_numpy(synth.features(tuple(new_feats.shape), seed=7)).to(DEV)
+        ((new_feats * w).sum() + (new_xyz.sum() if xyz_grad else 0.0)).backward()
+        outs.append(dict(feats=new_feats, inds=inds, fg=f.grad if cin else None, xg=x.grad if xyz_grad else None,
+                         params={k: p.grad for k, p in mod.named_parameters()},
+                         buffers={k: b.clone() for k, b in mod.named_buffers()}))
+    a, b = outs
+    assert torch.equal(a["inds"], b["inds"])
+    close(a["feats"], b["feats"], 1e-4, "forward")
+    if cin:
+        close(a["fg"], b["fg"], 1e-3, "d features")
+    if xyz_grad:
+        close(a["xg"], b["xg"], 1e-3, "d xyz")
+    for k in b["params"]:
+        close(a["params"][k], b["params"][k], 1e-3, "d " + k)
+    for k in b["buffers"]:
+        close(a["buffers"][k], b["buffers"][k], 1e-5, k)
