@@ -286,6 +286,26 @@ PTT_API int ptt_bn_relu_bwd(const float* dz, int ldz, const int* argmax_or_null,
                     int C, const float* ka, const float* kb, const float* mean, const float* rstd, const float* gamma,
                     double* sums, float* dy, int ld_dy, ptt_stream_t stream);
 
+/* Training of the kNN vector-attention block (variants.py:149-165): the forward is ptt_transformer_block_fwd with attn
+ * requested; these are the element kernels of its backward (ptt_b200/train_ops.py::_TransformerTrain), between the
+ * ptt_linear_fwd / ptt_linear_wgrad contractions.  Pair-row matrices (B*n*k, ld), token matrices (B*n, ldt).
+ * ptt_transformer_block_workspace_layout: float offsets of what the forward leaves in its workspace,
+ * h_out[0..6] = knn, x, qkv, res, g = relu(fc_gamma.0(.)), pos + v, ld. */
+PTT_API int ptt_transformer_block_workspace_layout(int B, int n, int k, int d_points, int d_model, size_t* h_out);
+/* dvp = attn * dres_i ;  dlogit = attn * (dres_i * vp - sum_j attn * dres_i * vp) / divisor   (softmax over the k rows of a token) */
+PTT_API int ptt_tr_softmax_bwd(const float* dres, int ldr, const float* attn, const float* vp, int ld, long long tokens, int k,
+                       int dm, float divisor, float* dlogit, float* dvp, ptt_stream_t stream);
+/* h1 = relu(fc_delta.0(xyz_i - xyz_j)), delta (pairs,4) = (xyz_i - xyz_j, 0), a_in = q_i - k_j + (vp_ij - v_j);
+ * delta0_w (dm,3) / delta0_b (dm) in nn.Linear layout; q, kk, v token matrices (B*n, ldt) */
+PTT_API int ptt_tr_pair_inputs(const float* xyz, const int* knn, int B, int n, int k, int dm, const float* delta0_w,
+                       const float* delta0_b, const float* q, const float* kk, const float* v, int ldt, const float* vp, int ld,
+                       float* h1, float* delta, float* a_in, ptt_stream_t stream);
+/* dy <- dy * [ref > 0], count floats (multiple of 4), same layout */
+PTT_API int ptt_tr_mask_positive(float* dy, const float* ref, long long count, ptt_stream_t stream);
+/* da <- da + dvp (= dpos) in place; dq_i = sum_j da_ij; dk[knn] -= da; dv[knn] += dvp (atomics; zero dk / dv first) */
+PTT_API int ptt_tr_pair_scatter(float* da, const float* dvp, int ld, const int* knn, int B, int n, int k, int dm, float* dq,
+                        float* dk, float* dv, int ldt, ptt_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * N3  The per-frame pre / post-processing of the tracking loop, for T independent tracklets at once
  *     (tools/eval_utils/eval_tracking_utils.py:140-274; ptt/datasets/kitti/kitti_tracking_utils.py:192-367).

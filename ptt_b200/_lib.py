@@ -70,6 +70,11 @@ SIGNATURES = {
     "ptt_sa_group_rows_grad": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_int, _P, _P, _P]),
     "ptt_bn_relu_maxpool": (c_int, [_P, c_int, ctypes.c_longlong, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
     "ptt_bn_relu_bwd": (c_int, [_P, c_int, _P, c_int, _P, c_int, ctypes.c_longlong, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
+    "ptt_transformer_block_workspace_layout": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "ptt_tr_softmax_bwd": (c_int, [_P, c_int, _P, _P, c_int, ctypes.c_longlong, c_int, c_int, c_float, _P, _P, _P]),
+    "ptt_tr_pair_inputs": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P]),
+    "ptt_tr_mask_positive": (c_int, [_P, _P, ctypes.c_longlong, _P]),
+    "ptt_tr_pair_scatter": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P]),
     "ptt_mt19937_stream": (c_int, [ctypes.c_uint, c_int, _P]),
     "ptt_track_crop": (c_int, [c_int, c_int, _PP, _PP, _PP, _IP, _IP, ctypes.c_double, ctypes.c_double, c_int, _P, c_int, _P, _P]),
     "ptt_track_regularize": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P]),

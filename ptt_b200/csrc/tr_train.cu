@@ -1,0 +1,142 @@
+// Backward-pass element kernels of the kNN vector-attention block (transformer_block/variants.py:149-165), the pieces
+// between the tensor-core contractions of ptt_b200/train_ops.py::_TransformerTrain:
+//
+//   forward (fused, tr_fused.cu)      res_i = sum_j p_ij (v_j + pos_ij),  p = softmax_j(fc_gamma(q_i - k_j + pos_ij) / sqrt(d))
+//   tr_softmax_bwd                    d(v+pos)_ij = p_ij dres_i ;  dlogit_ij = p_ij (dres_i (v+pos)_ij - sum_j' p_ij' dres_i (v+pos)_ij') / sqrt(d)
+//   tr_pair_inputs                    recomputes what the fused forward never stores: h1 = relu(fc_delta.0(xyz_i - xyz_j)),
+//                                     the 3-vector itself, and the attention input a = q_i - k_j + pos_ij
+//   tr_mask_positive                  dy <- dy * [ref > 0]   (ReLU backward against a stored activation)
+//   tr_pair_scatter                   dpos = da + d(v+pos);  dq_i = sum_j da_ij;  dk_j -= da_ij;  dv_j += d(v+pos)_ij  (atomics,
+//                                     like upstream's group_points_grad)
+#include "common.cuh"
+
+namespace {
+
+constexpr int TT = 256;
+inline unsigned tt_grid(long long total) { return (unsigned)llmin_((total + TT - 1) / TT, 148LL * 16); }
+
+__global__ void __launch_bounds__(TT) tr_softmax_bwd_kernel(const float* __restrict__ dres, int ldr, const float* __restrict__ attn,
+                                                             const float* __restrict__ vp, int ld, long long tokens, int k, int dm,
+                                                             float inv_div, float* __restrict__ dlogit, float* __restrict__ dvp) {
+  const long long total = tokens * dm;
+  for (long long e = (long long)blockIdx.x * TT + threadIdx.x; e < total; e += (long long)gridDim.x * TT) {
+    const long long tok = e / dm;
+    const int c = (int)(e - tok * dm);
+    const float dr = __ldg(dres + tok * ldr + c);
+    float dot = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const long long pr = tok * k + j;
+      dot = fmaf(__ldg(attn + pr * dm + c), dr * __ldg(vp + pr * ld + c), dot);
+    }
+    for (int j = 0; j < k; ++j) {
+      const long long pr = tok * k + j;
+      const float p = __ldg(attn + pr * dm + c);
+      dvp[pr * ld + c] = p * dr;
+      dlogit[pr * ld + c] = p * (dr * __ldg(vp + pr * ld + c) - dot) * inv_div;
+    }
+  }
+}
+
+// h1 (pairs, ld) = relu(Wd0 . delta + bd0), delta rows (pairs, 4) = (xyz_i - xyz_j, 0), a_in (pairs, ld) = q_i - k_j + vp_ij - v_j
+__global__ void __launch_bounds__(TT) tr_pair_inputs_kernel(const float* __restrict__ xyz, const int* __restrict__ knn, int n, int k,
+                                                             int dm, const float* __restrict__ wd0 /* (dm,3) */,
+                                                             const float* __restrict__ bd0, const float* __restrict__ q,
+                                                             const float* __restrict__ kk, const float* __restrict__ v, int ldt,
+                                                             const float* __restrict__ vp, int ld, long long pairs,
+                                                             float* __restrict__ h1, float* __restrict__ delta,
+                                                             float* __restrict__ a_in) {
+  const long long total = pairs * dm;
+  for (long long e = (long long)blockIdx.x * TT + threadIdx.x; e < total; e += (long long)gridDim.x * TT) {
+    const long long pr = e / dm;
+    const int c = (int)(e - pr * dm);
+    const long long tok = pr / k;
+    const long long b = tok / n;
+    const long long nb = b * n + __ldg(knn + pr);
+    const float dx = __ldg(xyz + tok * 3) - __ldg(xyz + nb * 3), dy = __ldg(xyz + tok * 3 + 1) - __ldg(xyz + nb * 3 + 1),
+                dz = __ldg(xyz + tok * 3 + 2) - __ldg(xyz + nb * 3 + 2);
+    float hv = bd0 ? __ldg(bd0 + c) : 0.f;
+    hv = fmaf(dx, __ldg(wd0 + c * 3), hv);
+    hv = fmaf(dy, __ldg(wd0 + c * 3 + 1), hv);
+    hv = fmaf(dz, __ldg(wd0 + c * 3 + 2), hv);
+    h1[pr * ld + c] = fmaxf(hv, 0.f);
+    if (c < 4) delta[pr * 4 + c] = c == 0 ? dx : (c == 1 ? dy : (c == 2 ? dz : 0.f));
+    a_in[pr * ld + c] = (__ldg(q + tok * ldt + c) - __ldg(kk + nb * ldt + c)) + (__ldg(vp + pr * ld + c) - __ldg(v + nb * ldt + c));
+  }
+}
+
+__global__ void __launch_bounds__(TT) tr_mask_positive_kernel(float* __restrict__ dy, const float* __restrict__ ref, long long total4) {
+  for (long long e = (long long)blockIdx.x * TT + threadIdx.x; e < total4; e += (long long)gridDim.x * TT) {
+    float4 d = reinterpret_cast<float4*>(dy)[e];
+    const float4 r = __ldg(reinterpret_cast<const float4*>(ref) + e);
+    d.x = r.x > 0.f ? d.x : 0.f; d.y = r.y > 0.f ? d.y : 0.f; d.z = r.z > 0.f ? d.z : 0.f; d.w = r.w > 0.f ? d.w : 0.f;
+    reinterpret_cast<float4*>(dy)[e] = d;
+  }
+}
+
+// one thread per (token, channel): da (pairs, ld) becomes dpos = da + dvp in place; dq (tokens, ldt) written; dk / dv (tokens,
+// ldt) accumulated with atomics (zero them first)
+__global__ void __launch_bounds__(TT) tr_pair_scatter_kernel(float* __restrict__ da, const float* __restrict__ dvp, int ld,
+                                                              const int* __restrict__ knn, int n, int k, int dm, long long tokens,
+                                                              float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
+                                                              int ldt) {
+  const long long total = tokens * dm;
+  for (long long e = (long long)blockIdx.x * TT + threadIdx.x; e < total; e += (long long)gridDim.x * TT) {
+    const long long tok = e / dm;
+    const int c = (int)(e - tok * dm);
+    const long long b = tok / n;
+    float sq = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const long long pr = tok * k + j;
+      const long long nb = b * n + __ldg(knn + pr);
+      const float a = da[pr * ld + c], p = __ldg(dvp + pr * ld + c);
+      sq += a;
+      atomicAdd(dk + nb * ldt + c, -a);
+      atomicAdd(dv + nb * ldt + c, p);
+      da[pr * ld + c] = a + p;
+    }
+    dq[tok * ldt + c] = sq;
+  }
+}
+
+}  // namespace
+
+extern "C" int ptt_tr_softmax_bwd(const float* dres, int ldr, const float* attn, const float* vp, int ld, long long tokens, int k,
+                                  int dm, float divisor, float* dlogit, float* dvp, ptt_stream_t stream) {
+  PTT_CHECK_ARG(tokens >= 0 && k >= 1 && dm >= 1 && ld >= dm && ldr >= dm && divisor > 0.f);
+  if (tokens == 0) return PTT_OK;
+  PTT_CHECK_ARG(dres && attn && vp && dlogit && dvp);
+  tr_softmax_bwd_kernel<<<tt_grid(tokens * dm), TT, 0, as_stream(stream)>>>(dres, ldr, attn, vp, ld, tokens, k, dm, 1.f / divisor,
+                                                                           dlogit, dvp); PTT_LAUNCHED();
+  return ptt_launch_status();
+}
+
+extern "C" int ptt_tr_pair_inputs(const float* xyz, const int* knn, int B, int n, int k, int dm, const float* delta0_w,
+                                  const float* delta0_b, const float* q, const float* kk, const float* v, int ldt,
+                                  const float* vp, int ld, float* h1, float* delta, float* a_in, ptt_stream_t stream) {
+  PTT_CHECK_ARG(B >= 0 && n >= 1 && k >= 1 && dm >= 4 && ld >= dm && ldt >= dm);
+  if (B == 0) return PTT_OK;
+  PTT_CHECK_ARG(xyz && knn && delta0_w && q && kk && v && vp && h1 && delta && a_in);
+  const long long pairs = (long long)B * n * k;
+  tr_pair_inputs_kernel<<<tt_grid(pairs * dm), TT, 0, as_stream(stream)>>>(xyz, knn, n, k, dm, delta0_w, delta0_b, q, kk, v, ldt, vp,
+                                                                          ld, pairs, h1, delta, a_in); PTT_LAUNCHED();
+  return ptt_launch_status();
+}
+
+extern "C" int ptt_tr_mask_positive(float* dy, const float* ref, long long count, ptt_stream_t stream) {
+  PTT_CHECK_ARG(count >= 0 && count % 4 == 0);
+  if (count == 0) return PTT_OK;
+  PTT_CHECK_ARG(dy && ref);
+  tr_mask_positive_kernel<<<tt_grid(count / 4), TT, 0, as_stream(stream)>>>(dy, ref, count / 4); PTT_LAUNCHED();
+  return ptt_launch_status();
+}
+
+extern "C" int ptt_tr_pair_scatter(float* da, const float* dvp, int ld, const int* knn, int B, int n, int k, int dm, float* dq,
+                                   float* dk, float* dv, int ldt, ptt_stream_t stream) {
+  PTT_CHECK_ARG(B >= 0 && n >= 1 && k >= 1 && dm >= 1 && ld >= dm && ldt >= dm);
+  if (B == 0) return PTT_OK;
+  PTT_CHECK_ARG(da && dvp && knn && dq && dk && dv);
+  const long long tokens = (long long)B * n;
+  tr_pair_scatter_kernel<<<tt_grid(tokens * dm), TT, 0, as_stream(stream)>>>(da, dvp, ld, knn, n, k, dm, tokens, dq, dk, dv, ldt);
+  PTT_LAUNCHED();
+  return ptt_launch_status();
+}

@@ -263,6 +263,17 @@ extern "C" size_t ptt_transformer_block_workspace_bytes(int B, int n, int k, int
   return W.total * sizeof(float);
 }
 
+// Float offsets of the activations the block leaves in its workspace (the training path's backward reads g and pos + v
+// from it): h_out[0..6] = knn, x, qkv, res, g (= relu(fc_gamma.0(.)), pairs x ld), pos + v (pairs x ld), ld
+extern "C" int ptt_transformer_block_workspace_layout(int B, int n, int k, int d_points, int d_model, size_t* h_out) {
+  TrLayout L;
+  TrWorkspace W;
+  PTT_CHECK_ARG(B > 0 && n > 0 && k > 0 && h_out && tr_layout(d_points, d_model, &L));
+  tr_workspace(B, n, k, L, &W);
+  h_out[0] = W.knn; h_out[1] = W.x; h_out[2] = W.qkv; h_out[3] = W.res; h_out[4] = W.h; h_out[5] = W.pos; h_out[6] = (size_t)W.ld;
+  return PTT_OK;
+}
+
 namespace {
 struct TrExtra {
   const float* q_features = nullptr;   // CrossAttentionBlock: the queries come from these (B, n, d_points) features

@@ -239,6 +239,7 @@ class TransformerBlock(_PackCache, nn.Module):
         self.w_vs = nn.Linear(d_model, d_model, bias=False)
         self.k = k
         self.return_attn = True      # the reference returns (res, attn); its callers use only [0]
+        self.native_train = True      # train() mode runs the native kernels; False: the reference's decomposition in torch
 
     def _pack(self):
         return self._cached(lambda: ops.PackedTransformer({k: v.detach() for k, v in self.state_dict().items()},
@@ -253,6 +254,10 @@ class TransformerBlock(_PackCache, nn.Module):
             r = ops.transformer_block_fwd(self._pack(), xyz, features, want_attn=self.return_attn)
             return r if self.return_attn else (r, None)
 
+        if self.training and self.native_train and self.VARIANT == 0:
+            from . import train_ops
+            if train_ops.transformer_train_supported(self, xyz, features):
+                return train_ops.transformer_train(self, xyz, features)      # forward AND backward on libptt_b200 kernels
         # the reference's decomposition (variants.py:149-165) with the kNN selection on our kernel
         knn_idx = ops.knn(xyz.detach(), self.k).long()
         B, n, _ = xyz.shape

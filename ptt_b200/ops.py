@@ -498,9 +498,10 @@ TRANSFORMER_KEYS = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc_delt
 class PackedTransformer:
     """TransformerBlock parameters (state_dict keys of variants.py:129-147) packed for ptt_transformer_block_fwd."""
 
-    def __init__(self, sd, k, variant=0):
+    def __init__(self, sd, k, variant=0, check_range=True):
         ts = [_req(sd[key].contiguous(), _F, sd[key].dim(), key) for key in TRANSFORMER_KEYS]
-        check_split_range("transformer block weight", *[t for t in ts if t.dim() == 2])
+        if check_range:
+            check_split_range("transformer block weight", *[t for t in ts if t.dim() == 2])
         self.d_model, self.d_points = ts[0].shape
         self.k = int(k)
         self.variant = int(variant)
@@ -510,7 +511,10 @@ class PackedTransformer:
             self.params = torch.empty(L.ptt_transformer_params_floats(self.d_points, self.d_model), dtype=_F, device=dev)
             check(L.ptt_transformer_pack_params(self.d_points, self.d_model, *[_ptr(t) for t in ts], _ptr(self.params),
                                                 _stream()), "ptt_transformer_pack_params")
-            torch.cuda.current_stream().synchronize()
+            if check_range:
+                torch.cuda.current_stream().synchronize()     # the .contiguous() temporaries may die after return
+            else:
+                self._keep = ts                               # training path: no sync; the sources stay referenced
 
     def workspace_bytes(self, B, n):
         return _lib.lib().ptt_transformer_block_workspace_bytes(B, n, self.k, self.d_points, self.d_model)

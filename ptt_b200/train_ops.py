@@ -187,3 +187,119 @@ def sa_train(xyz, feats_cm, new_xyz, idx, radius, normalize, mlp_module):
         bn.num_batches_tracked += 1
     out, _ = _SATrain.apply(xyz, feats_cm, new_xyz, idx, float(radius), bool(normalize), float(eps), float(momentum), *params)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# kNN vector-attention block (transformer_block/variants.py:127-165) in train() mode
+# ------------------------------------------------------------------------------------------------
+def _colsum(y, C):
+    return col_stats(y, C)[0].float()
+
+
+def _tr_layout(B, n, k, dp, dm):
+    out = (ctypes.c_size_t * 7)()
+    check(_lib.lib().ptt_transformer_block_workspace_layout(B, n, k, dp, dm, out), "ptt_transformer_block_workspace_layout")
+    return [int(v) for v in out]
+
+
+class _TransformerTrain(torch.autograd.Function):
+    """inputs: xyz (B,n,3), features (B,n,d_points), k, then the 15 parameters in ops.TRANSFORMER_KEYS order.
+    Forward = the fused eval kernels (there is no BatchNorm in the block) with attn and a kept workspace; backward
+    recomputes the cheap token-level projections, reads g = relu(fc_gamma.0(.)) and pos + v from that workspace and runs
+    the input / weight gradient contractions on tcgen05 (ptt_linear_fwd, ptt_linear_wgrad)."""
+
+    @staticmethod
+    def forward(ctx, xyz, features, k, *params):
+        sd = {key: p.detach() for key, p in zip(ops.TRANSFORMER_KEYS, params)}
+        packed = ops.PackedTransformer(sd, k, check_range=False)
+        B, n, dp = features.shape
+        knn = ops.knn(xyz, k)
+        with _DeviceGuard(xyz.device):
+            ws = torch.empty(packed.workspace_bytes(B, n) // 4 + 16, dtype=_F, device=xyz.device)
+        out, attn = ops.transformer_block_fwd(packed, xyz, features, knn_idx=knn, want_attn=True, workspace=ws)
+        ctx.save_for_backward(xyz, features, knn, attn, ws, *[p.detach() for p in params])
+        ctx.meta = (B, n, int(k), dp, packed.d_model)
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, dout, _dattn):
+        B, n, k, dp, dm = ctx.meta
+        sv = ctx.saved_tensors
+        xyz, features, knn, attn, ws = sv[:5]
+        W = dict(zip(ops.TRANSFORMER_KEYS, sv[5:]))
+        tokens, pairs = B * n, B * n * k
+        off = _tr_layout(B, n, k, dp, dm)
+        ld = off[6]
+        res = ws[off[3]: off[3] + tokens * ld].view(tokens, ld)
+        g = ws[off[4]: off[4] + pairs * ld].view(pairs, ld)
+        vp = ws[off[5]: off[5] + pairs * ld].view(pairs, ld)
+        lin = lambda w, b=None: ops.PackedLinear(w.contiguous(), b, check_range=False)
+        lin_t = lambda w: ops.PackedLinear(w.t().contiguous(), None, check_range=False)
+        f2 = features.reshape(tokens, dp)
+        dout2 = dout.reshape(tokens, dp).contiguous()
+        # token-level projections, recomputed (tokens x d_model each)
+        x = lin(W["fc1.weight"], W["fc1.bias"])(f2)
+        q, kk, v = lin(W["w_qs.weight"])(x), lin(W["w_ks.weight"])(x), lin(W["w_vs.weight"])(x)
+        with _DeviceGuard(xyz.device):
+            h1 = torch.empty(pairs, ld, dtype=_F, device=xyz.device)
+            delta = torch.empty(pairs, 4, dtype=_F, device=xyz.device)
+            a_in = torch.empty(pairs, ld, dtype=_F, device=xyz.device)
+            L = _lib.lib()
+            check(L.ptt_tr_pair_inputs(_ptr(xyz), _ptr(knn), B, n, k, dm, _ptr(W["fc_delta.0.weight"]), _ptr(W["fc_delta.0.bias"]),
+                                       _ptr(q), _ptr(kk), _ptr(v), dm, _ptr(vp), ld, _ptr(h1), _ptr(delta), _ptr(a_in), _stream()),
+                  "ptt_tr_pair_inputs")
+            grads = {}
+            # out = fc2(res) + features
+            grads["fc2.weight"] = linear_wgrad(dout2, res, dp, dm)
+            grads["fc2.bias"] = _colsum(dout2, dp)
+            dres = lin_t(W["fc2.weight"])(dout2)
+            dlogit = torch.empty(pairs, ld, dtype=_F, device=xyz.device)
+            dvp = torch.empty(pairs, ld, dtype=_F, device=xyz.device)
+            check(L.ptt_tr_softmax_bwd(_ptr(dres), dm, _ptr(attn), _ptr(vp), ld, tokens, k, dm, float(dm) ** 0.5, _ptr(dlogit),
+                                       _ptr(dvp), _stream()), "ptt_tr_softmax_bwd")
+            # logits = fc_gamma.2(g), g = relu(fc_gamma.0(a_in))
+            grads["fc_gamma.2.weight"] = linear_wgrad(dlogit, g, dm, dm)
+            grads["fc_gamma.2.bias"] = _colsum(dlogit, dm)
+            dpre = lin_t(W["fc_gamma.2.weight"])(dlogit)
+            check(L.ptt_tr_mask_positive(_ptr(dpre), _ptr(g), pairs * ld, _stream()), "ptt_tr_mask_positive")
+            grads["fc_gamma.0.weight"] = linear_wgrad(dpre, a_in, dm, dm)
+            grads["fc_gamma.0.bias"] = _colsum(dpre, dm)
+            da = lin_t(W["fc_gamma.0.weight"])(dpre)
+            # a_in = q_i - k_j + pos_ij ; vp = v_j + pos_ij
+            dq = torch.empty(tokens, dm, dtype=_F, device=xyz.device)
+            dk = torch.zeros(tokens, dm, dtype=_F, device=xyz.device)
+            dv = torch.zeros(tokens, dm, dtype=_F, device=xyz.device)
+            check(L.ptt_tr_pair_scatter(_ptr(da), _ptr(dvp), ld, _ptr(knn), B, n, k, dm, _ptr(dq), _ptr(dk), _ptr(dv), dm, _stream()),
+                  "ptt_tr_pair_scatter")
+            dpos = da
+            # pos = fc_delta.2(h1), h1 = relu(fc_delta.0(delta))
+            grads["fc_delta.2.weight"] = linear_wgrad(dpos, h1, dm, dm)
+            grads["fc_delta.2.bias"] = _colsum(dpos, dm)
+            dh1 = lin_t(W["fc_delta.2.weight"])(dpos)
+            check(L.ptt_tr_mask_positive(_ptr(dh1), _ptr(h1), pairs * ld, _stream()), "ptt_tr_mask_positive")
+            grads["fc_delta.0.weight"] = linear_wgrad(dh1, delta, dm, 3)
+            grads["fc_delta.0.bias"] = _colsum(dh1, dm)
+            # q, k, v = W x ; x = fc1(features)
+            grads["w_qs.weight"] = linear_wgrad(dq, x, dm, dm)
+            grads["w_ks.weight"] = linear_wgrad(dk, x, dm, dm)
+            grads["w_vs.weight"] = linear_wgrad(dv, x, dm, dm)
+            dx = lin_t(W["w_qs.weight"])(dq)
+            dx = lin_t(W["w_ks.weight"])(dk, residual=dx)
+            dx = lin_t(W["w_vs.weight"])(dv, residual=dx)
+            grads["fc1.weight"] = linear_wgrad(dx, f2, dm, dp)
+            grads["fc1.bias"] = _colsum(dx, dm)
+            df = lin_t(W["fc1.weight"])(dx, residual=dout2)
+        return (None, df.view(B, n, dp), None, *[grads[key].contiguous() for key in ops.TRANSFORMER_KEYS])
+
+
+def transformer_train_supported(block, xyz, features):
+    dm, dp, k = block.fc1.out_features, block.fc1.in_features, block.k
+    return (not xyz.requires_grad and dm in (64, 128, 256, 512) and dp % 4 == 0 and k >= 1 and (k & (k - 1)) == 0 and k <= 32
+            and xyz.shape[1] >= k)
+
+
+def transformer_train(block, xyz, features):
+    """TransformerBlock.forward in train() mode on the native path -> (res, attn)."""
+    params = [dict(block.named_parameters())[key] for key in ops.TRANSFORMER_KEYS]
+    return _TransformerTrain.apply(xyz, features, block.k, *params)

@@ -1,7 +1,15 @@
-"""GPU: the native training path (ptt_b200/train_ops.py; csrc/train_ops.cu, tc_wgrad.cu, tc_gemm.cu's operand transform)
-against torch autograd over the reference's decomposition (fp32, TF32 off): forward values, every gradient, the BatchNorm
-running statistics.  Tolerances: forward 1e-4 (north_star), gradients 1e-3 of the tensor's scale (sums over up to 10^5
-rows in a different order; the weight-gradient atomics are unordered)."""
+"""GPU: the native training path (ptt_b200/train_ops.py; csrc/train_ops.cu, tc_wgrad.cu, tr_train.cu, tc_gemm.cu's operand
+transform) against torch autograd over the reference's decomposition (fp32, TF32 off): forward values, every gradient,
+the BatchNorm running statistics.
+
+Tolerances.  Kernel-level checks (one op against torch on identical inputs): 1e-4 .. 2e-5 of the tensor's scale.
+Module-level gradients: a ReLU network's gradient is discontinuous where a pre-activation crosses zero, and two fp32
+implementations of the same forward differ by ~1e-6 there, so among the millions of activations of a full-size layer a
+handful get the other sub-gradient ("mask flips": measured 7 of 4.2 M at SA2).  Each flip moves one element of dy by
+O(1), i.e. a weight-gradient row by ~1e-2 of the gradient's scale -- both results are exact gradients of their own
+forward pass.  Module-level gradients are therefore compared in flip-robust metrics (cosine similarity and the
+fraction of entries outside 1e-3 of the scale) at full size, and in the max norm on layers small enough for flips not
+to occur."""
 import numpy as np
 import pytest
 import torch
@@ -99,6 +107,14 @@ def test_two_phase_batchnorm_and_pool_vs_torch():
         close(sums[1], gam.grad, 1e-4, "d gamma"), close(sums[0], bet.grad, 1e-4, "d beta")
 
 
+def close_grad(a, b, what="", cos_tol=3e-4, frac_tol=0.03):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    scale = max(float(b.abs().max()), 1e-9)
+    cos = float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30))
+    frac = float(((a - b).abs() > 1e-3 * scale).double().mean())
+    assert cos >= 1 - cos_tol and frac <= frac_tol, "%s: cosine %.6f, %.4f of the entries beyond 1e-3 of the scale" % (what, cos, frac)
+
+
 SA_TRAIN_CASES = [  # (B, N, C_in, mlp, npoint, radius, ns, xyz requires grad)
     (4, 512, 128, [128, 128, 128, 256], 256, 0.5, 32, False),        # ptt.yaml SA2
     (3, 1024, 0, [0, 64, 64, 128], 512, 0.3, 32, False),             # SA1: xyz only
@@ -130,11 +146,74 @@ def test_sa_module_native_training_vs_torch_decomposition(case):
     a, b = outs
     assert torch.equal(a["inds"], b["inds"])
     close(a["feats"], b["feats"], 1e-4, "forward")
+    small = B * npoint * ns * max(mlp) < 200000          # few enough activations for ReLU mask flips not to occur
+    cmp = (lambda x, y, w: close(x, y, 1e-3, w)) if small else close_grad
     if cin:
-        close(a["fg"], b["fg"], 1e-3, "d features")
+        cmp(a["fg"], b["fg"], "d features")
     if xyz_grad:
-        close(a["xg"], b["xg"], 1e-3, "d xyz")
+        cmp(a["xg"], b["xg"], "d xyz")
     for k in b["params"]:
-        close(a["params"][k], b["params"][k], 1e-3, "d " + k)
+        cmp(a["params"][k], b["params"][k], "d " + k)
     for k in b["buffers"]:
         close(a["buffers"][k], b["buffers"][k], 1e-5, k)
+
+
+@pytest.mark.parametrize("case", [(4, 128, 256, 512, 16), (3, 64, 256, 512, 16), (2, 48, 32, 64, 8), (2, 40, 64, 128, 4)])
+def test_transformer_block_native_training_vs_torch_decomposition(case):
+    from test_oracle_golden import transformer_state_dict
+    B, n, dp, dm, k = case
+    sd = {kk: t(v) for kk, v in synth.fill_state_dict(transformer_state_dict("TransformerBlock", dp, dm), seed=700 + n).items()}
+    xyz = torch.from_numpy(synth.make_clouds(B, n, 701 + n, "dense", role="template")).to(DEV)
+    feats = torch.from_numpy(synth.features((B, n, dp), seed=702 + n)).to(DEV)
+    w = torch.from_numpy(synth.features((B, n, dp), seed=703 + n)).to(DEV)
+    outs = []
+    for native in (True, False):
+        mod = modules.TransformerBlock(dp, dm, k)
+        mod.load_state_dict(sd)
+        mod = mod.to(DEV).train()
+        mod.native_train = native
+        f = feats.clone().requires_grad_(True)
+        res, attn = mod(xyz, f)
+        (res * w).sum().backward()
+        outs.append(dict(res=res, attn=attn, fg=f.grad, params={kk: p.grad for kk, p in mod.named_parameters()}))
+    a, b = outs
+    close(a["res"], b["res"], 1e-4, "forward")
+    close(a["attn"], b["attn"], 1e-4, "attn")
+    small = B * n * k * dm < 200000
+    cmp = (lambda x, y, what: close(x, y, 1e-3, what)) if small else close_grad
+    cmp(a["fg"], b["fg"], "d features")
+    for kk in b["params"]:
+        if kk == "fc_gamma.2.bias":          # constant over a token's neighbours: cancels in the softmax, gradient == 0
+            assert float(a["params"][kk].abs().max()) < 1e-3 and float(b["params"][kk].abs().max()) < 1e-3
+            continue
+        cmp(a["params"][kk], b["params"][kk], "d " + kk)
+
+
+def test_hot_path_net_train_step_native_vs_decomposition():
+    """The whole trainable hot path (ptt_b200/train.py::HotPathNet): one forward + backward on the native path against
+    the torch decomposition -- loss, a sample of gradients, BatchNorm running statistics (updated TWICE per step by the
+    siamese backbone, pointnet2_backbone.py:56-62)."""
+    from ptt_b200 import train
+    search = torch.from_numpy(synth.make_clouds(4, 1024, 800, "dense")).to(DEV)
+    template = torch.from_numpy(synth.make_clouds(4, 512, 801, "dense", role="template")).to(DEV)
+    got = []
+    for native in (True, False):
+        net = train.HotPathNet()
+        synth.load_filled(net, seed=0)
+        net = net.to(DEV).train()
+        for m in net.modules():
+            if hasattr(m, "native_train"):
+                m.native_train = native
+        out = net(search, template)
+        loss = sum((v.float() ** 2).mean() for v in out.values())
+        loss.backward()
+        got.append((float(loss), {k: p.grad for k, p in net.named_parameters()}, {k: b.clone() for k, b in net.named_buffers()}))
+    (la, ga, ba), (lb, gb, bb) = got
+    assert abs(la - lb) <= 1e-4 * abs(lb), (la, lb)
+    assert set(ga) == set(gb) and all(g is not None for g in ga.values())
+    for k in gb:
+        if k.endswith("fc_gamma.2.bias"):
+            continue
+        close_grad(ga[k], gb[k], "d " + k, cos_tol=2e-3, frac_tol=0.1)
+    for k in bb:
+        close(ba[k], bb[k], 1e-4, k)
