@@ -107,12 +107,12 @@ def test_two_phase_batchnorm_and_pool_vs_torch():
         close(sums[1], gam.grad, 1e-4, "d gamma"), close(sums[0], bet.grad, 1e-4, "d beta")
 
 
-def close_grad(a, b, what="", cos_tol=3e-4, frac_tol=0.03):
+def close_grad(a, b, what="", cos_tol=3e-4, l2_tol=2.5e-2):
+    """Flip-robust comparison (see the module docstring): direction and relative L2 distance of the two gradients."""
     a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
-    scale = max(float(b.abs().max()), 1e-9)
     cos = float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30))
-    frac = float(((a - b).abs() > 1e-3 * scale).double().mean())
-    assert cos >= 1 - cos_tol and frac <= frac_tol, "%s: cosine %.6f, %.4f of the entries beyond 1e-3 of the scale" % (what, cos, frac)
+    l2 = float((a - b).norm() / b.norm().clamp_min(1e-30))
+    assert cos >= 1 - cos_tol and l2 <= l2_tol, "%s: cosine %.6f, relative L2 distance %.2e" % (what, cos, l2)
 
 
 SA_TRAIN_CASES = [  # (B, N, C_in, mlp, npoint, radius, ns, xyz requires grad)
@@ -214,6 +214,6 @@ def test_hot_path_net_train_step_native_vs_decomposition():
     for k in gb:
         if k.endswith("fc_gamma.2.bias"):
             continue
-        close_grad(ga[k], gb[k], "d " + k, cos_tol=2e-3, frac_tol=0.1)
+        close_grad(ga[k], gb[k], "d " + k, cos_tol=1e-3, l2_tol=5e-2)
     for k in bb:
         close(ba[k], bb[k], 1e-4, k)
