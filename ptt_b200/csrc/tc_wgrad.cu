@@ -24,8 +24,6 @@
 namespace {
 
 constexpr int WG_THREADS = 288;          // 8 producer warps + MMA warp
-constexpr int WG_KB = 64;                // rows per k-block
-constexpr uint32_t WG_CHUNK = 8192;      // one 64-channel chunk of a k-block: 64 rows x 128 bytes
 
 struct WgArgs {
   const float* dy; int ldy;              // (R, >= M)
@@ -34,14 +32,14 @@ struct WgArgs {
   float* dw; int ldw;                    // (M, ldw >= N), accumulated into
   long long R;
   int M, N;
-  long long rows_per_cta;                // multiple of 64
+  long long rows_per_cta;                // multiple of the k-block height
 };
 
-// MN-major SWIZZLE_128B descriptor: 64-channel chunks LBO = 8 KB apart, 8-row groups SBO = 1 KB apart
-__device__ __forceinline__ uint64_t wg_desc(uint32_t smem_addr) {
+// MN-major SWIZZLE_128B descriptor: 64-channel chunks LBO apart, 8-row groups SBO = 1 KB apart
+__device__ __forceinline__ uint64_t wg_desc(uint32_t smem_addr, uint32_t chunk_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(WG_CHUNK >> 4) << 16;                // LBO
+  d |= (uint64_t)(chunk_bytes >> 4) << 16;             // LBO
   d |= (uint64_t)(1024 >> 4) << 32;                    // SBO
   d |= (uint64_t)1 << 46;                              // descriptor version 1 (Blackwell)
   d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
@@ -52,20 +50,25 @@ __host__ __device__ constexpr uint32_t wg_idesc(int M, int N) {
   return tc::idesc_f16<false>(M, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
 }
 
-template <int NT>                        // N tile = NT * 64 columns (NT = 1..5)
+// N tile = NT * 64 columns (NT = 1..5), M tile = MT * 128 channels (MT = 1, 2: two accumulators share the staged X rows,
+// which halves the re-reads of X when M >= 256), KBR = rows per k-block (64, or 32 where two stages of 64 do not fit)
+template <int NT, int MT, int KBR>
 struct WgCfg {
-  static constexpr uint32_t A_HALF = 2 * WG_CHUNK;                       // 128 channels
-  static constexpr uint32_t B_HALF = NT * WG_CHUNK;
+  static constexpr uint32_t CHUNK = KBR * 128;                           // 64 channels x KBR rows
+  static constexpr uint32_t A_HALF = 2 * MT * CHUNK;
+  static constexpr uint32_t B_HALF = NT * CHUNK;
   static constexpr uint32_t STAGE = 2 * A_HALF + 2 * B_HALF;
-  static constexpr int STAGES = 2;
+  static constexpr int STAGES = (3 * STAGE + 2048 <= 232448) ? 3 : 2;
   static constexpr uint32_t SMEM = STAGES * STAGE + 1024 + 256;
-  static constexpr int TMEM_COLS = NT <= 1 ? 64 : (NT <= 2 ? 128 : (NT <= 4 ? 256 : 512));
+  static constexpr int ACC_COLS = MT * NT * 64;
+  static constexpr int TMEM_COLS = ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512));
+  static_assert(ACC_COLS <= 512 && STAGES * STAGE + 2048 <= 232448, "tile does not fit TMEM / shared memory");
 };
 
-template <int NT>
+template <int NT, int MT, int KBR>
 __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ WgArgs a) {
-  using Cfg = WgCfg<NT>;
-  constexpr int BN = NT * 64;
+  using Cfg = WgCfg<NT, MT, KBR>;
+  constexpr int BN = NT * 64, BM = MT * 128;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ctrl = smem + Cfg::STAGES * Cfg::STAGE;
@@ -77,8 +80,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long r_begin = (long long)blockIdx.x * a.rows_per_cta;
   const long long r_end = r_begin + a.rows_per_cta < a.R ? r_begin + a.rows_per_cta : a.R;
-  const int m0 = blockIdx.y * 128, n0 = blockIdx.z * BN;
-  const int KB = r_end > r_begin ? (int)((r_end - r_begin + WG_KB - 1) / WG_KB) : 0;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.z * BN;
+  const int KB = r_end > r_begin ? (int)((r_end - r_begin + KBR - 1) / KBR) : 0;
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -99,24 +102,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
     int stage = 0;
     uint32_t phase = 0;
     const bool xform = a.x_ka != nullptr;
+    constexpr int AQ = BM / 4, BQ = BN / 4;             // float4 per dY / X row
+    constexpr int NA = (KBR * AQ + 255) / 256, NB = (KBR * BQ + 255) / 256;
     for (int kb = 0; kb < KB; ++kb) {
-      const long long rb = r_begin + (long long)kb * WG_KB;
-      // issue this k-block's global loads before waiting for the stage: dY 64 x 128, X 64 x BN (float4 granules)
-      float4 va[8];
+      const long long rb = r_begin + (long long)kb * KBR;
+      // this k-block's global loads are issued before waiting for the stage
+      float4 va[NA];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = (tid >> 5) + 8 * i, c4 = tid & 31;
+      for (int i = 0; i < NA; ++i) {
+        const int e = tid + 256 * i;
+        const int row = e / AQ, c4 = e - row * AQ;
         const long long r = rb + row;
         const int m = m0 + c4 * 4;
         va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < r_end && m < a.M) {
+        if (e < KBR * AQ && r < r_end && m < a.M) {
           const float* p = a.dy + r * a.ldy + m;
           if (m + 3 < a.M) va[i] = __ldg(reinterpret_cast<const float4*>(p));
           else { va[i].x = __ldg(p); if (m + 1 < a.M) va[i].y = __ldg(p + 1); if (m + 2 < a.M) va[i].z = __ldg(p + 2); }
         }
       }
-      constexpr int BQ = BN / 4;                       // float4 per X row
-      constexpr int NB = (64 * BQ + 255) / 256;        // float4 per thread
       float4 vb[NB];
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         const long long r = rb + row;
         const int n = n0 + c4 * 4;
         vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < 64 * BQ && r < r_end && n < a.N) {
+        if (e < KBR * BQ && r < r_end && n < a.N) {
           const float* p = a.x + r * a.ldx + n;
           if (n + 3 < a.N) vb[i] = __ldg(reinterpret_cast<const float4*>(p));
           else { vb[i].x = __ldg(p); if (n + 1 < a.N) vb[i].y = __ldg(p + 1); if (n + 2 < a.N) vb[i].z = __ldg(p + 2); }
@@ -143,24 +147,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
       uint8_t* b_hi = a_lo + Cfg::A_HALF;
       uint8_t* b_lo = b_hi + Cfg::B_HALF;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = (tid >> 5) + 8 * i, c4 = tid & 31;
-        uint2 ph, pl;
-        tc::split_f16x2(va[i].x, va[i].y, ph.x, pl.x);
-        tc::split_f16x2(va[i].z, va[i].w, ph.y, pl.y);
-        const uint32_t off = (uint32_t)(c4 >> 4) * WG_CHUNK + tc::sw128_offset(row, (c4 & 15) >> 1) + ((c4 & 1) << 3);
-        *reinterpret_cast<uint2*>(a_hi + off) = ph;
-        *reinterpret_cast<uint2*>(a_lo + off) = pl;
+      for (int i = 0; i < NA; ++i) {
+        const int e = tid + 256 * i;
+        if (e < KBR * AQ) {
+          const int row = e / AQ, c4 = e - row * AQ;
+          uint2 ph, pl;
+          tc::split_f16x2(va[i].x, va[i].y, ph.x, pl.x);
+          tc::split_f16x2(va[i].z, va[i].w, ph.y, pl.y);
+          const uint32_t off = (uint32_t)(c4 >> 4) * Cfg::CHUNK + tc::sw128_offset(row, (c4 & 15) >> 1) + ((c4 & 1) << 3);
+          *reinterpret_cast<uint2*>(a_hi + off) = ph;
+          *reinterpret_cast<uint2*>(a_lo + off) = pl;
+        }
       }
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
         const int e = tid + 256 * i;
-        if (e < 64 * BQ) {
+        if (e < KBR * BQ) {
           const int row = e / BQ, c4 = e - row * BQ;
           uint2 ph, pl;
           tc::split_f16x2(vb[i].x, vb[i].y, ph.x, pl.x);
           tc::split_f16x2(vb[i].z, vb[i].w, ph.y, pl.y);
-          const uint32_t off = (uint32_t)(c4 >> 4) * WG_CHUNK + tc::sw128_offset(row, (c4 & 15) >> 1) + ((c4 & 1) << 3);
+          const uint32_t off = (uint32_t)(c4 >> 4) * Cfg::CHUNK + tc::sw128_offset(row, (c4 & 15) >> 1) + ((c4 & 1) << 3);
           *reinterpret_cast<uint2*>(b_hi + off) = ph;
           *reinterpret_cast<uint2*>(b_lo + off) = pl;
         }
@@ -174,17 +181,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
       tc::mbar_wait(accum_full, 0);
       tc::tc_fence_after();
       const int quarter = warp & 3, chalf = warp >> 2;
-      const int m = m0 + quarter * 32 + lane;
-      constexpr int CH = BN / 2;                       // NT*32 columns per warp
+      constexpr int CH = Cfg::ACC_COLS / 2;            // accumulator columns per warp (both M halves laid side by side)
 #pragma unroll 1
       for (int c0 = chalf * CH; c0 < chalf * CH + CH; c0 += 32) {
         float v[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+        const int mt = c0 / BN, nc = c0 - mt * BN;     // which 128-channel half, column inside the N tile
+        const int m = m0 + mt * 128 + quarter * 32 + lane;
         if (m < a.M) {
-          float* row = a.dw + (size_t)m * a.ldw + n0 + c0;
+          float* row = a.dw + (size_t)m * a.ldw + n0 + nc;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < a.N) atomicAdd(row + j, v[j]);
+            if (n0 + nc + j < a.N) atomicAdd(row + j, v[j]);
         }
       }
     }
@@ -199,19 +207,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
       tc::mbar_wait(&full[stage], phase);
       tc::tc_fence_after();
       const uint32_t base = tc::smem_u32(smem + stage * Cfg::STAGE);
-      const uint64_t da_hi = wg_desc(base), da_lo = wg_desc(base + Cfg::A_HALF);
-      const uint64_t db_hi = wg_desc(base + 2 * Cfg::A_HALF), db_lo = wg_desc(base + 2 * Cfg::A_HALF + Cfg::B_HALF);
+      const uint64_t db_hi = wg_desc(base + 2 * Cfg::A_HALF, Cfg::CHUNK), db_lo = wg_desc(base + 2 * Cfg::A_HALF + Cfg::B_HALF, Cfg::CHUNK);
 #pragma unroll
-      for (int k = 0; k < WG_KB / 16; ++k) {
+      for (int k = 0; k < KBR / 16; ++k) {
         const uint64_t adv = (uint64_t)(k * (2048 >> 4));       // 16 rows = two 8-row groups = 2 KB
-        tc::mma_f16_w(tmem_base, da_hi + adv, db_hi + adv, IDESC1, (kb | k) != 0);
-        tc::mma_f16_w(tmem_base, da_lo + adv, db_hi + adv, IDESC1, 1);
-        tc::mma_f16_w(tmem_base, da_hi + adv, db_lo + adv, IDESC1, 1);
-        if (N2 > 0) {                                           // columns 256 .. BN-1: the chunks after the fourth
-          const uint64_t nb = (uint64_t)((4 * WG_CHUNK) >> 4);
-          tc::mma_f16_w(tmem_base + 256, da_hi + adv, db_hi + adv + nb, IDESC2, (kb | k) != 0);
-          tc::mma_f16_w(tmem_base + 256, da_lo + adv, db_hi + adv + nb, IDESC2, 1);
-          tc::mma_f16_w(tmem_base + 256, da_hi + adv, db_lo + adv + nb, IDESC2, 1);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint64_t da_hi = wg_desc(base + mt * 2 * Cfg::CHUNK, Cfg::CHUNK);
+          const uint64_t da_lo = wg_desc(base + Cfg::A_HALF + mt * 2 * Cfg::CHUNK, Cfg::CHUNK);
+          const uint32_t d = tmem_base + (uint32_t)(mt * BN);
+          tc::mma_f16_w(d, da_hi + adv, db_hi + adv, IDESC1, (kb | k) != 0);
+          tc::mma_f16_w(d, da_lo + adv, db_hi + adv, IDESC1, 1);
+          tc::mma_f16_w(d, da_hi + adv, db_lo + adv, IDESC1, 1);
+          if (N2 > 0) {                                         // columns 256 .. BN-1: the chunks after the fourth (MT == 1 only)
+            const uint64_t nb = (uint64_t)((4 * Cfg::CHUNK) >> 4);
+            tc::mma_f16_w(d + 256, da_hi + adv, db_hi + adv + nb, IDESC2, (kb | k) != 0);
+            tc::mma_f16_w(d + 256, da_lo + adv, db_hi + adv + nb, IDESC2, 1);
+            tc::mma_f16_w(d + 256, da_hi + adv, db_lo + adv + nb, IDESC2, 1);
+          }
         }
       }
       tc::mma_commit_w(&empty[stage]);
@@ -228,10 +241,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   }
 }
 
-template <int NT>
-int wg_launch(const WgArgs& a, int nsplit, int ntiles_n, cudaStream_t st) {
-  using Cfg = WgCfg<NT>;
-  auto kern = tc_wgrad_kernel<NT>;
+template <int NT, int MT, int KBR>
+int wg_launch(WgArgs a, int ntiles_n, cudaStream_t st) {
+  using Cfg = WgCfg<NT, MT, KBR>;
+  auto kern = tc_wgrad_kernel<NT, MT, KBR>;
   static bool configured[PTT_MAX_DEVICES] = {};
   const int dev = ptt_current_device();
   if (!configured[dev]) {
@@ -240,7 +253,16 @@ int wg_launch(const WgArgs& a, int nsplit, int ntiles_n, cudaStream_t st) {
     if (int rc = tc::tc_bind_fault(ptt_fault_word())) return rc;
     configured[dev] = true;
   }
-  dim3 grid(nsplit, ceil_div(a.M, 128), ntiles_n);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles_m = ceil_div(a.M, MT * 128);
+  const int tiles_mn = tiles_m * ntiles_n;
+  const long long kblocks = (a.R + KBR - 1) / KBR;
+  int nsplit = (int)llmin_(kblocks, (long long)((2 * sms + tiles_mn - 1) / tiles_mn));   // ~2 waves of CTAs
+  if (nsplit < 1) nsplit = 1;
+  a.rows_per_cta = ((kblocks + nsplit - 1) / nsplit) * KBR;
+  nsplit = (int)((a.R + a.rows_per_cta - 1) / a.rows_per_cta);
+  dim3 grid(nsplit, tiles_m, ntiles_n);
   kern<<<grid, WG_THREADS, Cfg::SMEM, st>>>(a); PTT_LAUNCHED();
   return ptt_launch_status();
 }
@@ -255,24 +277,28 @@ int ptt_tc_wgrad_launch(const float* dy, int ldy, const float* x, int ldx, const
     return PTT_ERR_UNSUPPORTED;                       // rows are read as float4
   WgArgs a;
   a.dy = dy; a.ldy = ldy; a.x = x; a.ldx = ldx; a.x_ka = x_ka; a.x_kb = x_kb;
-  a.dw = dw; a.ldw = ldw; a.R = R; a.M = M; a.N = N;
-  // N tiles of NT * 64 columns, NT <= 5 (320 columns: the 259 / 260-wide first layers fit one tile)
+  a.dw = dw; a.ldw = ldw; a.R = R; a.M = M; a.N = N; a.rows_per_cta = 0;
+  // Tile shape by HBM traffic per row (the kernel is bandwidth-bound): a CTA reads its rows of dY once per N tile and its
+  // rows of X once per M tile.  One accumulator (M tile 128, N tile <= 320) or two (M tile 256, N tile <= 256).
   const int chunks = ceil_div(N, 64);
-  const int ntiles = ceil_div(chunks, 5);
-  const int nt = ceil_div(chunks, ntiles);
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ptt_current_device());
-  const int tiles_mn = ceil_div(M, 128) * ntiles;
-  long long kblocks = (R + WG_KB - 1) / WG_KB;
-  int nsplit = (int)llmin_(kblocks, (long long)((2 * sms + tiles_mn - 1) / tiles_mn));   // ~2 waves of CTAs
-  if (nsplit < 1) nsplit = 1;
-  a.rows_per_cta = ((kblocks + nsplit - 1) / nsplit) * WG_KB;
-  nsplit = (int)((R + a.rows_per_cta - 1) / a.rows_per_cta);
+  const int nt1_tiles = ceil_div(chunks, 5), nt2_tiles = ceil_div(chunks, 4);
+  const long long traffic1 = (long long)M * nt1_tiles + (long long)N * ceil_div(M, 128);
+  const long long traffic2 = (long long)M * nt2_tiles + (long long)N * ceil_div(M, 256);
+  if (M > 128 && traffic2 < traffic1) {
+    const int nt = ceil_div(chunks, nt2_tiles);
+    switch (nt) {
+      case 1: return wg_launch<1, 2, 64>(a, nt2_tiles, st);
+      case 2: return wg_launch<2, 2, 64>(a, nt2_tiles, st);
+      case 3: return wg_launch<3, 2, 32>(a, nt2_tiles, st);
+      default: return wg_launch<4, 2, 32>(a, nt2_tiles, st);
+    }
+  }
+  const int nt = ceil_div(chunks, nt1_tiles);
   switch (nt) {
-    case 1: return wg_launch<1>(a, nsplit, ntiles, st);
-    case 2: return wg_launch<2>(a, nsplit, ntiles, st);
-    case 3: return wg_launch<3>(a, nsplit, ntiles, st);
-    case 4: return wg_launch<4>(a, nsplit, ntiles, st);
-    default: return wg_launch<5>(a, nsplit, ntiles, st);
+    case 1: return wg_launch<1, 1, 64>(a, nt1_tiles, st);
+    case 2: return wg_launch<2, 1, 64>(a, nt1_tiles, st);
+    case 3: return wg_launch<3, 1, 64>(a, nt1_tiles, st);
+    case 4: return wg_launch<4, 1, 64>(a, nt1_tiles, st);
+    default: return wg_launch<5, 1, 64>(a, nt1_tiles, st);
   }
 }

@@ -31,8 +31,10 @@ __device__ __forceinline__ void column_reduce(long long R, int C, double* out /*
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int u = 0; u < 4; ++u) acc[v][u] = 0.f;
-  if (slot < slots)
+  if (slot < slots) {
+#pragma unroll 4
     for (long long r = r0 + slot; r < r1; r += slots) row_values(r, c4 * 4, acc);
+  }
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     __syncthreads();

@@ -99,4 +99,4 @@ def time_train_step(device, world=1, rank=0, local_rank=0, batch=48, steps=5, wa
     torch.cuda.synchronize(device)
     return {"ms_per_step": e0.elapsed_time(e1) / steps, "steps": steps, "warmup": warmup, "batch_per_gpu": batch,
             "parameters": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
-            "loss_first_last": [float(losses[0]), float(losses[-1])]}
+            "loss_first_last": [float(losses[0].detach()), float(losses[-1].detach())]}

@@ -41,7 +41,7 @@ def close(a, b, tol, what=""):
 
 
 @pytest.mark.parametrize("R,M,N", [(5000, 128, 131), (64, 64, 3), (12345, 256, 259), (4096, 256, 128), (70000, 512, 512),
-                                   (300, 100, 36), (8200, 128, 64)])
+                                   (300, 100, 36), (8200, 128, 64), (9000, 256, 64), (3000, 512, 3), (2000, 384, 192)])
 def test_linear_wgrad_vs_torch(R, M, N):
     rs = np.random.RandomState(R + M)
     ldy, ldx = (M + 3) // 4 * 4, (N + 3) // 4 * 4
