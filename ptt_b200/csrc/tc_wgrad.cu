@@ -66,7 +66,7 @@ struct WgCfg {
 };
 
 template <int NT, int MT, int KBR>
-__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ WgArgs a) {
+__global__ void __maxnreg__(216) tc_wgrad_kernel(const __grid_constant__ WgArgs a) {
   using Cfg = WgCfg<NT, MT, KBR>;
   constexpr int BN = NT * 64, BM = MT * 128;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -99,15 +99,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 
   if (warp < 8) {
     // ------------------------------------------------------------ producers
+    // The k-block is staged in two halves of KBR / 2 rows, software-pipelined: the global loads of half h + 1 are in flight
+    // while half h is converted and stored, so the load latency is paid once per CTA, not once per k-block.
     int stage = 0;
     uint32_t phase = 0;
     const bool xform = a.x_ka != nullptr;
+    constexpr int HR = KBR / 2;
     constexpr int AQ = BM / 4, BQ = BN / 4;             // float4 per dY / X row
-    constexpr int NA = (KBR * AQ + 255) / 256, NB = (KBR * BQ + 255) / 256;
-    for (int kb = 0; kb < KB; ++kb) {
-      const long long rb = r_begin + (long long)kb * KBR;
-      // this k-block's global loads are issued before waiting for the stage
-      float4 va[NA];
+    constexpr int NA = (HR * AQ + 255) / 256, NB = (HR * BQ + 255) / 256;
+    auto load_half = [&](int hb, float4 (&va)[NA], float4 (&vb)[NB]) {
+      const long long rb = r_begin + (long long)hb * HR;
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
         const int e = tid + 256 * i;
@@ -115,13 +116,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         const long long r = rb + row;
         const int m = m0 + c4 * 4;
         va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < KBR * AQ && r < r_end && m < a.M) {
+        if (e < HR * AQ && r < r_end && m < a.M) {
           const float* p = a.dy + r * a.ldy + m;
           if (m + 3 < a.M) va[i] = __ldg(reinterpret_cast<const float4*>(p));
           else { va[i].x = __ldg(p); if (m + 1 < a.M) va[i].y = __ldg(p + 1); if (m + 2 < a.M) va[i].z = __ldg(p + 2); }
         }
       }
-      float4 vb[NB];
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
         const int e = tid + 256 * i;
@@ -129,19 +129,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         const long long r = rb + row;
         const int n = n0 + c4 * 4;
         vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < KBR * BQ && r < r_end && n < a.N) {
+        if (e < HR * BQ && r < r_end && n < a.N) {
           const float* p = a.x + r * a.ldx + n;
           if (n + 3 < a.N) vb[i] = __ldg(reinterpret_cast<const float4*>(p));
           else { vb[i].x = __ldg(p); if (n + 1 < a.N) vb[i].y = __ldg(p + 1); if (n + 2 < a.N) vb[i].z = __ldg(p + 2); }
-          if (xform) {
-            float* f = reinterpret_cast<float*>(&vb[i]);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (n + u < a.N) f[u] = fmaxf(fmaf(f[u], __ldg(a.x_ka + n + u), __ldg(a.x_kb + n + u)), 0.f);
-          }
         }
       }
-      tc::mbar_wait(&empty[stage], phase ^ 1);
+    };
+    auto store_half = [&](int half, float4 (&va)[NA], float4 (&vb)[NB]) {
       uint8_t* a_hi = smem + stage * Cfg::STAGE;
       uint8_t* a_lo = a_hi + Cfg::A_HALF;
       uint8_t* b_hi = a_lo + Cfg::A_HALF;
@@ -149,8 +144,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
         const int e = tid + 256 * i;
-        if (e < KBR * AQ) {
-          const int row = e / AQ, c4 = e - row * AQ;
+        if (e < HR * AQ) {
+          const int row = half * HR + e / AQ, c4 = e % AQ;
           uint2 ph, pl;
           tc::split_f16x2(va[i].x, va[i].y, ph.x, pl.x);
           tc::split_f16x2(va[i].z, va[i].w, ph.y, pl.y);
@@ -162,8 +157,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
         const int e = tid + 256 * i;
-        if (e < KBR * BQ) {
-          const int row = e / BQ, c4 = e - row * BQ;
+        if (e < HR * BQ) {
+          const int row = half * HR + e / BQ, c4 = e % BQ;
+          const int n = n0 + c4 * 4;
+          if (xform) {
+            float* f = reinterpret_cast<float*>(&vb[i]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) f[u] = n + u < a.N ? fmaxf(fmaf(f[u], __ldg(a.x_ka + n + u), __ldg(a.x_kb + n + u)), 0.f) : 0.f;
+          }
           uint2 ph, pl;
           tc::split_f16x2(vb[i].x, vb[i].y, ph.x, pl.x);
           tc::split_f16x2(vb[i].z, vb[i].w, ph.y, pl.y);
@@ -172,6 +173,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
           *reinterpret_cast<uint2*>(b_lo + off) = pl;
         }
       }
+    };
+    float4 va0[NA], vb0[NB], va1[NA], vb1[NB];
+    if (KB > 0) load_half(0, va0, vb0);
+    for (int kb = 0; kb < KB; ++kb) {
+      load_half(2 * kb + 1, va1, vb1);                   // rows beyond r_end load as zeros
+      tc::mbar_wait(&empty[stage], phase ^ 1);
+      store_half(0, va0, vb0);
+      if (kb + 1 < KB) load_half(2 * kb + 2, va0, vb0);
+      store_half(1, va1, vb1);
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&full[stage]);
       if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -289,8 +299,7 @@ int ptt_tc_wgrad_launch(const float* dy, int ldy, const float* x, int ldx, const
     switch (nt) {
       case 1: return wg_launch<1, 2, 64>(a, nt2_tiles, st);
       case 2: return wg_launch<2, 2, 64>(a, nt2_tiles, st);
-      case 3: return wg_launch<3, 2, 32>(a, nt2_tiles, st);
-      default: return wg_launch<4, 2, 32>(a, nt2_tiles, st);
+      default: break;                                   // wider N tiles: two stages of two accumulators do not fit shared memory
     }
   }
   const int nt = ceil_div(chunks, nt1_tiles);
