@@ -66,7 +66,7 @@ struct WgCfg {
 };
 
 template <int NT, int MT, int KBR>
-__global__ void __maxnreg__(216) tc_wgrad_kernel(const __grid_constant__ WgArgs a) {
+__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ WgArgs a) {
   using Cfg = WgCfg<NT, MT, KBR>;
   constexpr int BN = NT * 64, BM = MT * 128;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
