@@ -487,6 +487,7 @@ def run_b200(a):
                                                     "batch 1 with a host round trip per frame"}
                 del hp1
             del trk
+        track["per_gpu"] = True          # every rank advances its own T tracklets; the figures are rank 0's
         track["what"] = ("BatchedTracker: %d frames per tracklet, ~4200 raw points per frame (padded to %d), crop + resample + "
                          "whole tracker forward + box update in one CUDA graph per frame, H2D of the raw clouds staged one frame "
                          "ahead; wall clock" % (n_frames - 1, cap))
