@@ -258,6 +258,12 @@ PTT_API int ptt_transformer_std_fwd(const float* xyz, const float* features, int
 /* ptt_linear_fwd with the A operand transformed on load: x <- relu(a_ka[k] * x + a_kb[k]) (both NULL: plain). */
 PTT_API int ptt_linear_fwd_ex(const float* x, int ldx, int R, int K, const float* a_ka, const float* a_kb, const float* params,
                       int Cout, int relu, const float* residual, int ldr, float* y, int ldy, ptt_stream_t stream);
+/* ptt_linear_fwd_ex (no activation, no residual) + the column statistics of its result in one call: sums_or_null (2,Cout)
+ * double <- sum_r y and sum_r y*y.  Bias-free layers (has_bias == 0) over >= 4096 rows with K, Cout <= 260 / 256 run on a
+ * weight-stationary persistent kernel that produces the statistics in its epilogue (csrc/ws_gemm.cu). */
+PTT_API int ptt_linear_fwd_stats(const float* x, int ldx, long long R, int K, const float* a_ka, const float* a_kb,
+                         const float* params, int Cout, int has_bias, float* y, int ldy, double* sums_or_null,
+                         ptt_stream_t stream);
 /* Weight gradient: dw (M,ldw)[:, 0:N] += dy (R,ldy)[:, 0:M]^T . f(x (R,ldx)[:, 0:N]), f = identity or relu(ka*x + kb)
  * per column of x; tcgen05 with MN-major operands, split over the rows, fp32 atomics into dw (zero it first). */
 PTT_API int ptt_linear_wgrad(const float* dy, int ldy, const float* x, int ldx, const float* x_ka, const float* x_kb,

@@ -54,6 +54,12 @@ static inline size_t ptt_tc_weight_floats(int K, int Cout) { return ptt_tc_weigh
 int ptt_tc_wgrad_launch(const float* dy, int ldy, const float* x, int ldx, const float* x_ka, const float* x_kb,
                         long long R, int M, int N, float* dw, int ldw, cudaStream_t st);
 
+// Weight-stationary persistent contraction with fused column statistics (ws_gemm.cu): y = f(x) . W^T (no bias), optional
+// sums (2, N) double <- column sums of y and y^2.  wimg = the ptt_tc_pack_weight image of W (N, K).
+bool ptt_ws_gemm_supported(const float* x, int ldx, long long R, int K, int N);
+int ptt_ws_gemm_launch(const float* x, int ldx, long long R, int K, const float* ka, const float* kb, const void* wimg, int N,
+                       float* y, int ldy, double* sums, cudaStream_t st);
+
 // nn.Linear (Cout,K) weight [+bias] -> transposed image (K+1 rows x ldw, last row = bias), zero padded
 int ptt_linear_pack_launch(const float* weight, const float* bias, int K, int Cout, float* params, cudaStream_t st);
 // same, into columns [col0, col0+Cout) of an image whose rows are ldw wide (caller zero-fills the image)

@@ -238,6 +238,8 @@ int grid_rows(long long work, int per_block) {
 
 }  // namespace
 
+extern "C" int ptt_col_stats(const float* y, int ldy, long long R, int C, double* sums, ptt_stream_t stream);
+
 extern "C" int ptt_linear_fwd_ex(const float* x, int ldx, int R, int K, const float* a_ka, const float* a_kb,
                                  const float* params, int Cout, int relu, const float* residual, int ldr, float* y, int ldy,
                                  ptt_stream_t stream) {
@@ -253,6 +255,31 @@ extern "C" int ptt_linear_fwd_ex(const float* x, int ldx, int R, int K, const fl
   a.residual = residual; a.ldr = ldr;
   a.y = y; a.ldy = ldy;
   return ptt_gemm_launch(a, as_stream(stream));
+}
+
+// y = f(x) . W^T [+ bias]; sums_or_null (2, Cout) double <- column sums of y and y^2 (phase 1 of the two-phase BatchNorm).
+// Bias-free layers over many rows run on the weight-stationary persistent kernel, whose transposed epilogue produces the
+// statistics for free; everything else is ptt_linear_fwd_ex followed by the column reduction.
+extern "C" int ptt_linear_fwd_stats(const float* x, int ldx, long long R, int K, const float* a_ka, const float* a_kb,
+                                    const float* params, int Cout, int has_bias, float* y, int ldy, double* sums_or_null,
+                                    ptt_stream_t stream) {
+  PTT_CHECK_ARG(R >= 0 && R <= 0x7fffffffLL && K >= 1 && Cout >= 1 && ldx >= K && ldy >= Cout &&
+                ((a_ka == nullptr) == (a_kb == nullptr)));
+  cudaStream_t st = as_stream(stream);
+  if (R == 0) {
+    if (sums_or_null != nullptr) {
+      cudaError_t e = cudaMemsetAsync(sums_or_null, 0, (size_t)2 * Cout * sizeof(double), st);
+      if (e != cudaSuccess) return (int)e;
+    }
+    return PTT_OK;
+  }
+  PTT_CHECK_ARG(x && params && y);
+  const int ldw = ptt_linear_ldw(Cout);
+  if (!has_bias && ptt_ws_gemm_supported(x, ldx, R, K, Cout))
+    return ptt_ws_gemm_launch(x, ldx, R, K, a_ka, a_kb, params + (size_t)(K + 1) * ldw, Cout, y, ldy, sums_or_null, st);
+  int rc = ptt_linear_fwd_ex(x, ldx, (int)R, K, a_ka, a_kb, params, Cout, 0, nullptr, 0, y, ldy, stream);
+  if (rc != PTT_OK || sums_or_null == nullptr) return rc;
+  return ptt_col_stats(y, ldy, R, Cout, sums_or_null, stream);
 }
 
 extern "C" int ptt_linear_wgrad(const float* dy, int ldy, const float* x, int ldx, const float* x_ka, const float* x_kb,

@@ -284,6 +284,7 @@ class PackedLinear:
     def __init__(self, weight, bias=None, check_range=True):
         _req(weight, _F, 2, "weight")
         self.cout, self.k = weight.shape
+        self.has_bias = bias is not None
         if check_range:
             check_split_range("linear weight", weight)
         L = _lib.lib()
@@ -297,6 +298,7 @@ class PackedLinear:
         _req(weight, _F, 2, "weight")
         if tuple(weight.shape) != (self.cout, self.k):
             raise PttError("repack: weight must be (%d,%d)" % (self.cout, self.k))
+        self.has_bias = bias is not None
         with _DeviceGuard(weight.device):
             check(_lib.lib().ptt_linear_pack(_ptr(weight), _ptr(bias), self.k, self.cout, _ptr(self.params), _stream()),
                   "ptt_linear_pack")
@@ -331,6 +333,23 @@ class PackedLinear:
             check(_lib.lib().ptt_linear_fwd_ex(_ptr(x), ldx, R, self.k, _ptr(ka), _ptr(kb), _ptr(self.params), self.cout, int(relu),
                                                _ptr(residual), ldr, _ptr(y), ldy, _stream()), "ptt_linear_fwd_ex")
         return y
+
+
+def linear_with_stats(lin, x, in_affine=None, want_stats=True, ld_out=None):
+    """y = lin(f(x)) without activation / residual, plus (optionally) the column sums of y and y*y as a (2, Cout) float64
+    tensor (ptt_linear_fwd_stats: bias-free layers over many rows take the weight-stationary persistent kernel)."""
+    _req(x, _F, 2, "x")
+    R, ldx = x.shape
+    if ldx < lin.k:
+        raise PttError("linear: x has %d columns, weight expects %d" % (ldx, lin.k))
+    ka, kb = in_affine if in_affine is not None else (None, None)
+    ldy = lin.cout if ld_out is None else int(ld_out)
+    with _DeviceGuard(x.device):
+        y = torch.empty(R, ldy, dtype=_F, device=x.device) if ldy == lin.cout else torch.zeros(R, ldy, dtype=_F, device=x.device)
+        sums = torch.empty(2, lin.cout, dtype=torch.float64, device=x.device) if want_stats else None
+        check(_lib.lib().ptt_linear_fwd_stats(_ptr(x), ldx, R, lin.k, _ptr(ka), _ptr(kb), _ptr(lin.params), lin.cout,
+                                              int(lin.has_bias), _ptr(y), ldy, _ptr(sums), _stream()), "ptt_linear_fwd_stats")
+    return y, sums
 
 
 class PackedConvStack:

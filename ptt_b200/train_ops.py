@@ -123,8 +123,8 @@ class _SATrain(torch.autograd.Function):
             w, g, b, rm, rv = params[5 * l: 5 * l + 5]
             cout = w.shape[0]
             lin = ops.PackedLinear(w.detach().reshape(cout, k_in).contiguous(), None, check_range=False)
-            y = lin(src, in_affine=aff)
-            ka, kb, mean, rstd = bn_train_finalize(col_stats(y, cout), R, g.detach(), b.detach(), eps, momentum, rm, rv)
+            y, sums = ops.linear_with_stats(lin, src, in_affine=aff)      # the statistics come out of the contraction's epilogue
+            ka, kb, mean, rstd = bn_train_finalize(sums, R, g.detach(), b.detach(), eps, momentum, rm, rv)
             ys.append(y)
             affs.append((ka, kb))
             stats.append((mean, rstd))
@@ -161,7 +161,7 @@ class _SATrain(torch.autograd.Function):
             need_dx = l > 0 or ctx.needs_input_grad[0] or (C > 0 and ctx.needs_input_grad[1]) or ctx.needs_input_grad[2]
             if need_dx:
                 wt = ops.PackedLinear(ws[l].reshape(cout, cin).t().contiguous(), None, check_range=False)
-                dz = wt(dy, ld_out=_pad4(cin))
+                dz, _ = ops.linear_with_stats(wt, dy, want_stats=False, ld_out=_pad4(cin))
         d_xyz = d_feats = d_new = None
         if ctx.needs_input_grad[0] or (C > 0 and ctx.needs_input_grad[1]) or ctx.needs_input_grad[2]:
             want_xyz = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]

@@ -217,3 +217,28 @@ def test_hot_path_net_train_step_native_vs_decomposition():
         close_grad(ga[k], gb[k], "d " + k, cos_tol=1e-3, l2_tol=5e-2)
     for k in bb:
         close(ba[k], bb[k], 1e-4, k)
+
+
+@pytest.mark.parametrize("R,K,N", [(50000, 128, 128), (40001, 64, 64), (33000, 3, 64), (20000, 131, 128), (12345, 260, 128),
+                                   (30000, 128, 256), (9000, 256, 131), (5000, 64, 3), (70000, 128, 64), (2000, 128, 128),
+                                   (8000, 256, 512)])
+def test_linear_with_stats_weight_stationary_and_fallback(R, K, N):
+    """ptt_linear_fwd_stats: the weight-stationary persistent kernel (bias-free, >= 4096 rows, N <= 256) and the tc_gemm +
+    column-reduction fallback (small R, N = 512, biased layers) against torch, incl. the fused statistics, the operand
+    transform, ragged last tiles and padded output rows."""
+    rs = np.random.RandomState(R % 1000 + K)
+    ldx, ldy = (K + 3) // 4 * 4, (N + 3) // 4 * 4
+    x = torch.from_numpy(rs.standard_normal((R, ldx)).astype(np.float32)).to(DEV)
+    w = torch.from_numpy((rs.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)).to(DEV)
+    ka = torch.from_numpy(rs.uniform(0.5, 1.5, K).astype(np.float32)).to(DEV)
+    kb = torch.from_numpy(rs.normal(0, 0.5, K).astype(np.float32)).to(DEV)
+    for bias in (None, torch.from_numpy(rs.normal(0, 0.3, N).astype(np.float32)).to(DEV)):
+        lin = ops.PackedLinear(w, bias)
+        for aff in (None, (ka, kb)):
+            xin = x[:, :K].double() if aff is None else torch.relu(x[:, :K] * ka + kb).double()
+            want = xin @ w.double().t() + (bias.double() if bias is not None else 0.0)
+            y, sums = ops.linear_with_stats(lin, x, in_affine=aff, ld_out=ldy)
+            close(y[:, :N], want, 2e-5, "y")
+            assert ldy == N or not y[:, N:].any()
+            close(sums[0], want.sum(0), 1e-4, "sum y")
+            close(sums[1], (want * want).sum(0), 1e-4, "sum y^2")
