@@ -13,9 +13,9 @@
 // Grid: (row chunks [split-K], 128-channel tiles of M, tiles of N).  A CTA reduces ITS rows into a TMEM accumulator
 // (128 lanes x NT*64 columns) and adds it to dW with fp32 atomics (the order of those additions is not fixed, like the
 // atomicAdd scatter of upstream's group_points_grad; the differences are ~1e-7 relative).
-//   warps 0-7  producers: fp32 rows of dY and X -> (optional per-channel affine + ReLU on X) -> fp16 hi/lo -> smem;
-//              afterwards the epilogue (TMEM -> registers -> atomicAdd)
-//   warp  8    TMEM allocation + tcgen05.mma issue
+//   warps 0-15 producers: fp32 rows of dY and X -> (optional per-channel affine + ReLU on X) -> fp16 hi/lo -> smem;
+//              warps 0-7 afterwards run the epilogue (TMEM -> registers -> atomicAdd)
+//   warp  16   TMEM allocation + tcgen05.mma issue
 // The X operand can be given as the PRE-activation of the producing layer: x = relu(ka[n] * y[r, n] + kb[n]) is applied
 // while the rows are staged (BatchNorm + ReLU of the training path), so normalised activations are never stored.
 #include "gemm.cuh"
@@ -23,7 +23,8 @@
 
 namespace {
 
-constexpr int WG_THREADS = 288;          // 8 producer warps + MMA warp
+constexpr int WG_PROD = 512;             // 16 producer warps: the staging is load-latency bound, more warps = more loads in flight
+constexpr int WG_THREADS = WG_PROD + 32;  // + the MMA warp
 
 struct WgArgs {
   const float* dy; int ldy;              // (R, >= M)
@@ -85,19 +86,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      tc::mbar_init(&full[s], 256);
+      tc::mbar_init(&full[s], WG_PROD);
       tc::mbar_init(&empty[s], 1);
     }
     tc::mbar_init(accum_full, 1);
     tc::mbar_init_fence();
   }
-  if (warp == 8) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == WG_PROD / 32) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
+  if (warp < WG_PROD / 32) {
     // ------------------------------------------------------------ producers
     // The k-block is staged in two halves of KBR / 2 rows, software-pipelined: the global loads of half h + 1 are in flight
     // while half h is converted and stored, so the load latency is paid once per CTA, not once per k-block.
@@ -106,12 +107,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
     const bool xform = a.x_ka != nullptr;
     constexpr int HR = KBR / 2;
     constexpr int AQ = BM / 4, BQ = BN / 4;             // float4 per dY / X row
-    constexpr int NA = (HR * AQ + 255) / 256, NB = (HR * BQ + 255) / 256;
+    constexpr int NA = (HR * AQ + WG_PROD - 1) / WG_PROD, NB = (HR * BQ + WG_PROD - 1) / WG_PROD;
     auto load_half = [&](int hb, float4 (&va)[NA], float4 (&vb)[NB]) {
       const long long rb = r_begin + (long long)hb * HR;
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
-        const int e = tid + 256 * i;
+        const int e = tid + WG_PROD * i;
         const int row = e / AQ, c4 = e - row * AQ;
         const long long r = rb + row;
         const int m = m0 + c4 * 4;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
       }
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
-        const int e = tid + 256 * i;
+        const int e = tid + WG_PROD * i;
         const int row = e / BQ, c4 = e - row * BQ;
         const long long r = rb + row;
         const int n = n0 + c4 * 4;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
       uint8_t* b_lo = b_hi + Cfg::B_HALF;
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
-        const int e = tid + 256 * i;
+        const int e = tid + WG_PROD * i;
         if (e < HR * AQ) {
           const int row = half * HR + e / AQ, c4 = e % AQ;
           uint2 ph, pl;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
       }
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
-        const int e = tid + 256 * i;
+        const int e = tid + WG_PROD * i;
         if (e < HR * BQ) {
           const int row = half * HR + e / BQ, c4 = e % BQ;
           const int n = n0 + c4 * 4;
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
       if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
     // ------------------------------------------------------------ epilogue: warp w -> lane quarter w % 4, column half w / 4
-    if (KB > 0) {
+    if (KB > 0 && warp < 8) {
       tc::mbar_wait(accum_full, 0);
       tc::tc_fence_after();
       const int quarter = warp & 3, chalf = warp >> 2;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == WG_PROD / 32) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
