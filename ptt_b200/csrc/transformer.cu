@@ -67,15 +67,17 @@ __global__ void tr_cprime_kernel(const float* __restrict__ wg0, const float* __r
   cprime[c] = acc;
 }
 
-// out[c] = sum_m w[c * ldw + m] * v[m]   (v == nullptr: out = 0)
+// out[c] = sum_m w[c * ldw + m] * v[m]   (v == nullptr: out = 0); one warp per output row
 __global__ void tr_matvec_kernel(const float* __restrict__ w, int ldw, const float* __restrict__ v, int rows, int K,
                                  float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= rows) return;
   float acc = 0.f;
   if (v)
-    for (int m = 0; m < K; ++m) acc = fmaf(w[(size_t)c * ldw + m], v[m], acc);
-  out[c] = acc;
+    for (int m = lane; m < K; m += 32) acc = fmaf(w[(size_t)c * ldw + m], v[m], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[c] = acc;
 }
 
 // h[(b,i,j), c] = relu(Wd0[c,:] . (xyz_i - xyz_knn(i,j)) + bd0[c])      delta0 image: 3 rows wt + bias row
@@ -247,7 +249,7 @@ extern "C" int ptt_transformer_pack_params(int d_points, int d_model, const floa
       g.wt = T; g.ldw = ldp; g.N = dp;
       g.y = P; g.ldy = dp;
       if ((rc = ptt_gemm_launch_ffma(g, st))) return rc;
-      tr_matvec_kernel<<<ceil_div(dm, 128), 128, 0, st>>>(mats[i], dm, fc1_b, dm, dm, bv); PTT_LAUNCHED();
+      tr_matvec_kernel<<<ceil_div(dm * 32, 128), 128, 0, st>>>(mats[i], dm, fc1_b, dm, dm, bv); PTT_LAUNCHED();
       if ((rc = ptt_linear_pack_cols(P, bv, dp, dm, 3 * ld, i * ld, params + L.qkg1, st))) return rc;
     }
     if ((rc = tc_pack(L.qkg1, dp, 3 * ld))) return rc;
