@@ -265,9 +265,11 @@ PTT_API int ptt_linear_fwd_stats(const float* x, int ldx, long long R, int K, co
                          const float* params, int Cout, int has_bias, float* y, int ldy, double* sums_or_null,
                          ptt_stream_t stream);
 /* Weight gradient: dw (M,ldw)[:, 0:N] += dy (R,ldy)[:, 0:M]^T . f(x (R,ldx)[:, 0:N]), f = identity or relu(ka*x + kb)
- * per column of x; tcgen05 with MN-major operands, split over the rows, fp32 atomics into dw (zero it first). */
+ * per column of x; tcgen05 with MN-major operands, split over the rows, fp32 atomics into dw (zero it first).
+ * dbias_or_null (M floats, zero it first) += column sums of dy -- the bias gradient of the same layer, accumulated from
+ * the rows of dy while they are staged for the contraction (no second pass over dy). */
 PTT_API int ptt_linear_wgrad(const float* dy, int ldy, const float* x, int ldx, const float* x_ka, const float* x_kb,
-                     long long R, int M, int N, float* dw, int ldw, ptt_stream_t stream);
+                     long long R, int M, int N, float* dw, int ldw, float* dbias_or_null, ptt_stream_t stream);
 /* sums (2,C) double <- column sums of y and y*y over R rows (phase 1 of the two-phase BatchNorm). */
 PTT_API int ptt_col_stats(const float* y, int ldy, long long R, int C, double* sums, ptt_stream_t stream);
 /* Phase 2: mean / biased variance from sums -> ka = gamma*rstd, kb = beta - mean*ka, mean, rstd (C floats each);

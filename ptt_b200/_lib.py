@@ -64,7 +64,7 @@ SIGNATURES = {
     "ptt_transformer_std_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "ptt_linear_fwd_ex": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_int, _P, c_int, _P]),
     "ptt_linear_fwd_stats": (c_int, [_P, c_int, ctypes.c_longlong, c_int, _P, _P, _P, c_int, c_int, _P, c_int, _P, _P]),
-    "ptt_linear_wgrad": (c_int, [_P, c_int, _P, c_int, _P, _P, ctypes.c_longlong, c_int, c_int, _P, c_int, _P]),
+    "ptt_linear_wgrad": (c_int, [_P, c_int, _P, c_int, _P, _P, ctypes.c_longlong, c_int, c_int, _P, c_int, _P, _P]),
     "ptt_col_stats": (c_int, [_P, c_int, ctypes.c_longlong, c_int, _P, _P]),
     "ptt_bn_train_finalize": (c_int, [_P, ctypes.c_longlong, c_int, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
     "ptt_sa_group_rows": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_int, _P]),

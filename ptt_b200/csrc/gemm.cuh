@@ -50,9 +50,10 @@ int ptt_tc_gemm_launch(const PttGemmArgs& a, const void* wimg, cudaStream_t st);
 static inline size_t ptt_tc_weight_floats(int K, int Cout) { return ptt_tc_weight_halves(K, Cout) / 2; }
 
 // Weight gradient (tc_wgrad.cu): dW (M, ldw)[:, 0:N] += dY (R, ldy)[:, 0:M]^T . f(X (R, ldx)[:, 0:N]), f = identity or
-// relu(ka[n] * x + kb[n]); rows are read as float4 (ldy, ldx multiples of 4, 16-byte aligned bases)
+// relu(ka[n] * x + kb[n]); rows are read as float4 (ldy, ldx multiples of 4, 16-byte aligned bases).  dbias (optional, M
+// floats) += column sums of dY: the bias gradient of the same layer, taken from the rows while they are staged.
 int ptt_tc_wgrad_launch(const float* dy, int ldy, const float* x, int ldx, const float* x_ka, const float* x_kb,
-                        long long R, int M, int N, float* dw, int ldw, cudaStream_t st);
+                        long long R, int M, int N, float* dw, int ldw, float* dbias, cudaStream_t st);
 
 // Weight-stationary persistent contraction with fused column statistics (ws_gemm.cu): y = f(x) . W^T (no bias), optional
 // sums (2, N) double <- column sums of y and y^2.  wimg = the ptt_tc_pack_weight image of W (N, K).

@@ -129,11 +129,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
       tc::mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < Cfg::NRA; ++s) {
-      tc::mbar_init(&ha_full[s], 256);
+      tc::mbar_init(&ha_full[s], 8);
       tc::mbar_init(&ha_free[s], 1);
     }
     for (int s = 0; s < Cfg::NRB; ++s) {
-      tc::mbar_init(&hb_full[s], 256);
+      tc::mbar_init(&hb_full[s], 8);
       tc::mbar_init(&hb_free[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
         }
         tc::tc_fence_before();
         tc::fence_proxy_async_smem();
-        tc::mbar_arrive(&hb_full[sb]);
+        tc::mbar_arrive_warp(&hb_full[sb]);
         if (++sb == Cfg::NRB) { sb = 0; pb ^= 1; }
       }
       if (erec) a.dbg[1000 + it * 4 + 1] = clock64();
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
           *reinterpret_cast<uint2*>(blk + 16384 + off) = lo;
         }
         tc::fence_proxy_async_smem();
-        tc::mbar_arrive(&ha_full[sa]);
+        tc::mbar_arrive_warp(&ha_full[sa]);
         if (++sa == Cfg::NRA) { sa = 0; pa ^= 1; }
 #pragma unroll
         for (int i = 0; i < 8; ++i) gcur[i] = gnxt[i];

@@ -22,6 +22,13 @@ __device__ __forceinline__ void mbar_init_fence() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per WARP: every lane has finished (and fenced) its part, lane 0 signals for all 32 (the barrier is initialised
+// with the number of warps).  An mbarrier arrival is a serialised shared-memory atomic: 256 or 512 per-thread arrivals per
+// pipeline stage cost more than the stage's MMAs (measured on tc_wgrad: 1.2 us per 64-row k-block with nothing else to do).
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
                "r"(bytes)

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(&full_a[s], 256);
+      tc::mbar_init(&full_a[s], 8);
       tc::mbar_init(&full_b[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         *reinterpret_cast<uint2*>(a_lo + off) = pl;
       }
       tc::fence_proxy_async_smem();
-      tc::mbar_arrive(&full_a[stage]);
+      tc::mbar_arrive_warp(&full_a[stage]);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];

@@ -31,9 +31,11 @@ struct WgArgs {
   const float* x; int ldx;               // (R, >= N)
   const float* x_ka; const float* x_kb;  // optional per-channel affine (+ ReLU) applied to x on load; both or neither
   float* dw; int ldw;                    // (M, ldw >= N), accumulated into
+  float* dbias;                          // optional (M): += column sums of dY (the bias gradient of the same layer)
   long long R;
   int M, N;
   long long rows_per_cta;                // multiple of the k-block height
+  int vec4;                              // dw rows are 16-byte aligned and ldw % 4 == 0: vector reductions
 };
 
 // MN-major SWIZZLE_128B descriptor: 64-channel chunks LBO apart, 8-row groups SBO = 1 KB apart
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      tc::mbar_init(&full[s], WG_PROD);
+      tc::mbar_init(&full[s], WG_PROD / 32);          // one arrival per producer warp
       tc::mbar_init(&empty[s], 1);
     }
     tc::mbar_init(accum_full, 1);
@@ -100,14 +102,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 
   if (warp < WG_PROD / 32) {
     // ------------------------------------------------------------ producers
-    // The k-block is staged in two halves of KBR / 2 rows, software-pipelined: the global loads of half h + 1 are in flight
-    // while half h is converted and stored, so the load latency is paid once per CTA, not once per k-block.
+    // The k-block is staged in two halves of KBR / 2 rows, software-pipelined: the global loads of the following halves are
+    // in flight while half h is converted and stored, so the load latency is paid once per CTA, not once per k-block.
     int stage = 0;
     uint32_t phase = 0;
     const bool xform = a.x_ka != nullptr;
     constexpr int HR = KBR / 2;
     constexpr int AQ = BM / 4, BQ = BN / 4;             // float4 per dY / X row
     constexpr int NA = (HR * AQ + WG_PROD - 1) / WG_PROD, NB = (HR * BQ + WG_PROD - 1) / WG_PROD;
+    static_assert(WG_PROD % AQ == 0, "a producer thread keeps its dY columns over all its rows");
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);       // column sums of this thread's 4 dY channels (bias gradient)
     auto load_half = [&](int hb, float4 (&va)[NA], float4 (&vb)[NB]) {
       const long long rb = r_begin + (long long)hb * HR;
 #pragma unroll
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         const int e = tid + WG_PROD * i;
         if (e < HR * AQ) {
           const int row = half * HR + e / AQ, c4 = e % AQ;
+          bsum.x += va[i].x; bsum.y += va[i].y; bsum.z += va[i].z; bsum.w += va[i].w;
           uint2 ph, pl;
           tc::split_f16x2(va[i].x, va[i].y, ph.x, pl.x);
           tc::split_f16x2(va[i].z, va[i].w, ph.y, pl.y);
@@ -175,17 +180,40 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         }
       }
     };
-    float4 va0[NA], vb0[NB], va1[NA], vb1[NB];
-    if (KB > 0) load_half(0, va0, vb0);
-    for (int kb = 0; kb < KB; ++kb) {
-      load_half(2 * kb + 1, va1, vb1);                   // rows beyond r_end load as zeros
-      tc::mbar_wait(&empty[stage], phase ^ 1);
-      store_half(0, va0, vb0);
-      if (kb + 1 < KB) load_half(2 * kb + 2, va0, vb0);
-      store_half(1, va1, vb1);
-      tc::fence_proxy_async_smem();
-      tc::mbar_arrive(&full[stage]);
-      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+    constexpr int KD = (NA + NB) <= 3 ? 2 : 1;            // k-blocks held in registers (see below)
+    // KD k-blocks (2 * KD halves) live in registers: narrow tiles move few bytes per half, so they keep two k-blocks of
+    // loads in flight to cover the HBM latency; wide tiles already have > 64 KB outstanding with one.  (An L2 bulk
+    // prefetch several k-blocks ahead was measured too: no gain, the register-level loads already cover the latency.)
+    float4 va[KD][2][NA], vb[KD][2][NB];
+#pragma unroll
+    for (int d = 0; d < KD; ++d)
+      if (d < KB) {
+        load_half(2 * d, va[d][0], vb[d][0]);
+        load_half(2 * d + 1, va[d][1], vb[d][1]);          // rows beyond r_end load as zeros
+      }
+    for (int kb0 = 0; kb0 < KB; kb0 += KD) {
+#pragma unroll
+      for (int d = 0; d < KD; ++d) {
+        const int kb = kb0 + d;
+        if (kb < KB) {
+          const bool more = kb + KD < KB;
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          store_half(0, va[d][0], vb[d][0]);
+          if (more) load_half(2 * (kb + KD), va[d][0], vb[d][0]);
+          store_half(1, va[d][1], vb[d][1]);
+          if (more) load_half(2 * (kb + KD) + 1, va[d][1], vb[d][1]);
+          tc::fence_proxy_async_smem();                     // every writer publishes its stores to the async proxy ...
+          tc::mbar_arrive_warp(&full[stage]);               // ... and one lane per warp signals: 16 arrivals per k-block, not 512
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    if (a.dbias != nullptr && blockIdx.z == 0) {          // rows beyond r_end and channels beyond M were staged as zeros
+      const int m = m0 + (tid % AQ) * 4;
+      const float bs[4] = {bsum.x, bsum.y, bsum.z, bsum.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (m + u < a.M) atomicAdd(a.dbias + m + u, bs[u]);
     }
     // ------------------------------------------------------------ epilogue: warp w -> lane quarter w % 4, column half w / 4
     if (KB > 0 && warp < 8) {
@@ -200,10 +228,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         const int mt = c0 / BN, nc = c0 - mt * BN;     // which 128-channel half, column inside the N tile
         const int m = m0 + mt * 128 + quarter * 32 + lane;
         if (m < a.M) {
+          // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the L2 atomic operations.  ldw % 4 == 0, so a
+          // group that straddles N only adds the zeros staged for the padding columns.
           float* row = a.dw + (size_t)m * a.ldw + n0 + nc;
+          if (a.vec4) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + nc + j < a.N) atomicAdd(row + j, v[j]);
+            for (int j = 0; j < 32; j += 4)
+              if (n0 + nc + j < a.N) atomicAdd(reinterpret_cast<float4*>(row + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + nc + j < a.N) atomicAdd(row + j, v[j]);
+          }
         }
       }
     }
@@ -280,15 +316,17 @@ int wg_launch(WgArgs a, int ntiles_n, cudaStream_t st) {
 
 }  // namespace
 
-// dW (M, ldw)[:, 0:N] += dY (R, ldy)[:, 0:M]^T . f(X (R, ldx)[:, 0:N]);  f = identity, or relu(ka * x + kb) per column
+// dW (M, ldw)[:, 0:N] += dY (R, ldy)[:, 0:M]^T . f(X (R, ldx)[:, 0:N]);  f = identity, or relu(ka * x + kb) per column;
+// dbias (M, optional) += column sums of dY
 int ptt_tc_wgrad_launch(const float* dy, int ldy, const float* x, int ldx, const float* x_ka, const float* x_kb,
-                        long long R, int M, int N, float* dw, int ldw, cudaStream_t st) {
+                        long long R, int M, int N, float* dw, int ldw, float* dbias, cudaStream_t st) {
   if (R <= 0 || M <= 0 || N <= 0) return PTT_OK;
   if ((ldy % 4) || (ldx % 4) || (reinterpret_cast<uintptr_t>(dy) & 15u) || (reinterpret_cast<uintptr_t>(x) & 15u))
     return PTT_ERR_UNSUPPORTED;                       // rows are read as float4
   WgArgs a;
   a.dy = dy; a.ldy = ldy; a.x = x; a.ldx = ldx; a.x_ka = x_ka; a.x_kb = x_kb;
-  a.dw = dw; a.ldw = ldw; a.R = R; a.M = M; a.N = N; a.rows_per_cta = 0;
+  a.vec4 = (ldw % 4 == 0) && (reinterpret_cast<uintptr_t>(dw) & 15u) == 0;
+  a.dw = dw; a.ldw = ldw; a.dbias = dbias; a.R = R; a.M = M; a.N = N; a.rows_per_cta = 0;
   // Tile shape by HBM traffic per row (the kernel is bandwidth-bound): a CTA reads its rows of dY once per N tile and its
   // rows of X once per M tile.  One accumulator (M tile 128, N tile <= 320) or two (M tile 256, N tile <= 256).
   const int chunks = ceil_div(N, 64);

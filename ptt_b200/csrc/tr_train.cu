@@ -64,6 +64,42 @@ __global__ void __launch_bounds__(TT) tr_pair_inputs_kernel(const float* __restr
   }
 }
 
+// the same, 4 channels per thread (dm, ld, ldt multiples of 4; 16-byte aligned bases): 16-byte accesses, 32-bit index math
+__global__ void __launch_bounds__(TT) tr_pair_inputs_v4_kernel(const float* __restrict__ xyz, const int* __restrict__ knn, int n, int k,
+                                                                int dm, const float* __restrict__ wd0, const float* __restrict__ bd0,
+                                                                const float* __restrict__ q, const float* __restrict__ kk,
+                                                                const float* __restrict__ v, int ldt, const float* __restrict__ vp,
+                                                                int ld, unsigned pairs, float* __restrict__ h1,
+                                                                float* __restrict__ delta, float* __restrict__ a_in) {
+  const unsigned q4 = (unsigned)dm / 4;
+  const unsigned total = pairs * q4;
+  for (unsigned e = blockIdx.x * TT + threadIdx.x; e < total; e += gridDim.x * TT) {
+    const unsigned pr = e / q4;
+    const int c = (int)(e - pr * q4) * 4;
+    const unsigned tok = pr / (unsigned)k;
+    const unsigned nb = (tok / (unsigned)n) * (unsigned)n + (unsigned)__ldg(knn + pr);
+    const float dx = __ldg(xyz + (size_t)tok * 3) - __ldg(xyz + (size_t)nb * 3), dy = __ldg(xyz + (size_t)tok * 3 + 1) - __ldg(xyz + (size_t)nb * 3 + 1),
+                dz = __ldg(xyz + (size_t)tok * 3 + 2) - __ldg(xyz + (size_t)nb * 3 + 2);
+    float hv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float t = bd0 ? __ldg(bd0 + c + u) : 0.f;
+      t = fmaf(dx, __ldg(wd0 + (c + u) * 3), t);
+      t = fmaf(dy, __ldg(wd0 + (c + u) * 3 + 1), t);
+      t = fmaf(dz, __ldg(wd0 + (c + u) * 3 + 2), t);
+      hv[u] = fmaxf(t, 0.f);
+    }
+    *reinterpret_cast<float4*>(h1 + (size_t)pr * ld + c) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    if (c == 0) *reinterpret_cast<float4*>(delta + (size_t)pr * 4) = make_float4(dx, dy, dz, 0.f);
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(q + (size_t)tok * ldt + c));
+    const float4 kv = __ldg(reinterpret_cast<const float4*>(kk + (size_t)nb * ldt + c));
+    const float4 pv = __ldg(reinterpret_cast<const float4*>(vp + (size_t)pr * ld + c));
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(v + (size_t)nb * ldt + c));
+    *reinterpret_cast<float4*>(a_in + (size_t)pr * ld + c) =
+        make_float4((qv.x - kv.x) + (pv.x - vv.x), (qv.y - kv.y) + (pv.y - vv.y), (qv.z - kv.z) + (pv.z - vv.z), (qv.w - kv.w) + (pv.w - vv.w));
+  }
+}
+
 __global__ void __launch_bounds__(TT) tr_mask_positive_kernel(float* __restrict__ dy, const float* __restrict__ ref, long long total4) {
   for (long long e = (long long)blockIdx.x * TT + threadIdx.x; e < total4; e += (long long)gridDim.x * TT) {
     float4 d = reinterpret_cast<float4*>(dy)[e];
@@ -98,6 +134,35 @@ __global__ void __launch_bounds__(TT) tr_pair_scatter_kernel(float* __restrict__
   }
 }
 
+// 4 channels per thread; the scatter uses 16-byte vector reductions (red.global.add.v4.f32)
+__global__ void __launch_bounds__(TT) tr_pair_scatter_v4_kernel(float* __restrict__ da, const float* __restrict__ dvp, int ld,
+                                                                 const int* __restrict__ knn, int n, int k, int dm, unsigned tokens,
+                                                                 float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
+                                                                 int ldt) {
+  const unsigned q4 = (unsigned)dm / 4;
+  const unsigned total = tokens * q4;
+  for (unsigned e = blockIdx.x * TT + threadIdx.x; e < total; e += gridDim.x * TT) {
+    const unsigned tok = e / q4;
+    const int c = (int)(e - tok * q4) * 4;
+    const unsigned b0 = (tok / (unsigned)n) * (unsigned)n;
+    float4 sq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int j = 0; j < k; ++j) {
+      const size_t pr = (size_t)tok * k + j;
+      const size_t nb = b0 + (unsigned)__ldg(knn + pr);
+      float4* ap = reinterpret_cast<float4*>(da + pr * ld + c);
+      const float4 a = *ap, p = __ldg(reinterpret_cast<const float4*>(dvp + pr * ld + c));
+      sq.x += a.x; sq.y += a.y; sq.z += a.z; sq.w += a.w;
+      atomicAdd(reinterpret_cast<float4*>(dk + nb * ldt + c), make_float4(-a.x, -a.y, -a.z, -a.w));
+      atomicAdd(reinterpret_cast<float4*>(dv + nb * ldt + c), p);
+      *ap = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    }
+    *reinterpret_cast<float4*>(dq + (size_t)tok * ldt + c) = sq;
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 }  // namespace
 
 extern "C" int ptt_tr_softmax_bwd(const float* dres, int ldr, const float* attn, const float* vp, int ld, long long tokens, int k,
@@ -117,6 +182,13 @@ extern "C" int ptt_tr_pair_inputs(const float* xyz, const int* knn, int B, int n
   if (B == 0) return PTT_OK;
   PTT_CHECK_ARG(xyz && knn && delta0_w && q && kk && v && vp && h1 && delta && a_in);
   const long long pairs = (long long)B * n * k;
+  if (dm % 4 == 0 && ld % 4 == 0 && ldt % 4 == 0 && pairs * (dm / 4) < 0x7fffffffLL && aligned16(q) && aligned16(kk) && aligned16(v) &&
+      aligned16(vp) && aligned16(h1) && aligned16(delta) && aligned16(a_in)) {
+    tr_pair_inputs_v4_kernel<<<tt_grid(pairs * (dm / 4)), TT, 0, as_stream(stream)>>>(xyz, knn, n, k, dm, delta0_w, delta0_b, q, kk, v,
+                                                                                     ldt, vp, ld, (unsigned)pairs, h1, delta, a_in);
+    PTT_LAUNCHED();
+    return ptt_launch_status();
+  }
   tr_pair_inputs_kernel<<<tt_grid(pairs * dm), TT, 0, as_stream(stream)>>>(xyz, knn, n, k, dm, delta0_w, delta0_b, q, kk, v, ldt, vp,
                                                                           ld, pairs, h1, delta, a_in); PTT_LAUNCHED();
   return ptt_launch_status();
@@ -136,6 +208,13 @@ extern "C" int ptt_tr_pair_scatter(float* da, const float* dvp, int ld, const in
   if (B == 0) return PTT_OK;
   PTT_CHECK_ARG(da && dvp && knn && dq && dk && dv);
   const long long tokens = (long long)B * n;
+  if (dm % 4 == 0 && ld % 4 == 0 && ldt % 4 == 0 && tokens * k * (dm / 4) < 0x7fffffffLL && aligned16(da) && aligned16(dvp) && aligned16(dq) &&
+      aligned16(dk) && aligned16(dv)) {
+    tr_pair_scatter_v4_kernel<<<tt_grid(tokens * (dm / 4)), TT, 0, as_stream(stream)>>>(da, dvp, ld, knn, n, k, dm, (unsigned)tokens, dq,
+                                                                                       dk, dv, ldt);
+    PTT_LAUNCHED();
+    return ptt_launch_status();
+  }
   tr_pair_scatter_kernel<<<tt_grid(tokens * dm), TT, 0, as_stream(stream)>>>(da, dvp, ld, knn, n, k, dm, tokens, dq, dk, dv, ldt);
   PTT_LAUNCHED();
   return ptt_launch_status();

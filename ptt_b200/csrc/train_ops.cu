@@ -92,22 +92,28 @@ __global__ void __launch_bounds__(TO_THREADS) sa_group_rows_kernel2(const float*
                                                                      const int* __restrict__ idx, int N, int M, int ns, int C,
                                                                      float radius, int normalize, long long rows,
                                                                      float* __restrict__ out, int ld) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (long long)blockIdx.x * (TO_THREADS / 32) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (TO_THREADS / 32);
-  for (long long r = warp; r < rows; r += nwarps) {
+  // one thread per float4 of an output row (ld % 4 == 0): consecutive threads write consecutive 16-byte pieces
+  const unsigned q4 = (unsigned)ld / 4;
+  const long long total = rows * q4;
+  for (long long e = (long long)blockIdx.x * TO_THREADS + threadIdx.x; e < total; e += (long long)gridDim.x * TO_THREADS) {
+    const long long r = e / q4;
+    const int c0 = (int)(e - r * q4) * 4;
     const long long cj = r / ns;                          // (b, j)
     const long long b = cj / M;
-    const int i = __ldg(idx + r);
-    float* o = out + r * ld;
-    if (lane < 3) {
-      float v = __fsub_rn(__ldg(xyz + (b * N + i) * 3 + lane), __ldg(new_xyz + cj * 3 + lane));
-      if (normalize) v = __fdiv_rn(v, radius);
-      o[lane] = v;
+    const long long src = b * N + __ldg(idx + r);
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u;
+      if (c < 3) {
+        float v = __fsub_rn(__ldg(xyz + src * 3 + c), __ldg(new_xyz + cj * 3 + c));
+        if (normalize) v = __fdiv_rn(v, radius);
+        o[u] = v;
+      } else {
+        o[u] = c < 3 + C ? __ldg(feats + src * (long long)ldf + (c - 3)) : 0.f;
+      }
     }
-    const float* f = feats + (b * N + i) * (long long)ldf;
-    for (int c = lane; c < C; c += 32) o[3 + c] = __ldg(f + c);
-    for (int c = 3 + C + lane; c < ld; c += 32) o[c] = 0.f;
+    *reinterpret_cast<float4*>(out + r * ld + c0) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -174,16 +180,32 @@ struct BnBwd {
   long long R; int C;
 };
 
-__device__ __forceinline__ void bn_bwd_m(const BnBwd& p, long long r, int c, float (&m)[4], float (&yh)[4]) {
-  const float4 v = __ldg(reinterpret_cast<const float4*>(p.y + r * p.ldy + c));
+struct BnChan {                           // the per-channel terms of 4 consecutive channels
+  float a[4], b[4], mu[4], rs[4];
+};
+
+__device__ __forceinline__ BnChan bn_chan(const BnBwd& p, int c) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p.ka + c)), b = __ldg(reinterpret_cast<const float4*>(p.kb + c));
   const float4 mu = __ldg(reinterpret_cast<const float4*>(p.mean + c)), rs = __ldg(reinterpret_cast<const float4*>(p.rstd + c));
-  const float yv[4] = {v.x, v.y, v.z, v.w}, av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-  const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
+  BnChan ch = {{a.x, a.y, a.z, a.w}, {b.x, b.y, b.z, b.w}, {mu.x, mu.y, mu.z, mu.w}, {rs.x, rs.y, rs.z, rs.w}};
+  return ch;
+}
+
+__device__ __forceinline__ void bn_bwd_m(const BnBwd& p, const BnChan& ch, long long r, int c, float (&m)[4], float (&yh)[4]) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p.y + r * p.ldy + c));
+  const float yv[4] = {v.x, v.y, v.z, v.w};
   float d[4];
   if (p.arg != nullptr) {
-    const long long g = r / p.ns;
-    const int s = (int)(r - g * p.ns);
+    long long g;
+    int s;
+    if (p.R <= 0x7fffffffLL) {              // 32-bit division (the 64-bit one is emulated)
+      const unsigned gu = (unsigned)r / (unsigned)p.ns;
+      g = gu;
+      s = (int)((unsigned)r - gu * (unsigned)p.ns);
+    } else {
+      g = r / p.ns;
+      s = (int)(r - g * p.ns);
+    }
     const int4 ai = __ldg(reinterpret_cast<const int4*>(p.arg + g * p.C + c));
     const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dz + g * p.ldz + c));
     d[0] = ai.x == s ? dv.x : 0.f; d[1] = ai.y == s ? dv.y : 0.f; d[2] = ai.z == s ? dv.z : 0.f; d[3] = ai.w == s ? dv.w : 0.f;
@@ -193,15 +215,16 @@ __device__ __forceinline__ void bn_bwd_m(const BnBwd& p, long long r, int c, flo
   }
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    m[u] = fmaf(yv[u], av[u], bv[u]) > 0.f ? d[u] : 0.f;
-    yh[u] = (yv[u] - muv[u]) * rsv[u];
+    m[u] = fmaf(yv[u], ch.a[u], ch.b[u]) > 0.f ? d[u] : 0.f;
+    yh[u] = (yv[u] - ch.mu[u]) * ch.rs[u];
   }
 }
 
 __global__ void __launch_bounds__(TO_THREADS) bn_relu_bwd_reduce_kernel(const BnBwd p, double* __restrict__ sums) {
+  const BnChan ch = bn_chan(p, (threadIdx.x % (p.C / 4)) * 4);   // column_reduce gives a thread the same 4 channels every row
   column_reduce<2>(p.R, p.C, sums, [&](long long r, int c, float (&acc)[2][4]) {
     float m[4], yh[4];
-    bn_bwd_m(p, r, c, m, yh);
+    bn_bwd_m(p, ch, r, c, m, yh);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       acc[0][u] += m[u];
@@ -214,20 +237,44 @@ __global__ void __launch_bounds__(TO_THREADS) bn_relu_bwd_reduce_kernel(const Bn
 __global__ void __launch_bounds__(TO_THREADS) bn_relu_bwd_apply_kernel(const BnBwd p, const double* __restrict__ sums,
                                                                         const float* __restrict__ gamma, float* __restrict__ dy,
                                                                         int ld_dy) {
-  const long long total = p.R * (p.C / 4);
+  const int tpr = p.C / 4;                                  // threads per row
   const double inv_r = 1.0 / (double)p.R;
-  for (long long e = (long long)blockIdx.x * TO_THREADS + threadIdx.x; e < total; e += (long long)gridDim.x * TO_THREADS) {
-    const long long r = e / (p.C / 4);
-    const int c = (int)(e - r * (p.C / 4)) * 4;
-    float m[4], yh[4], o[4];
-    bn_bwd_m(p, r, c, m, yh);
+  auto coefficients = [&](int c, float (&gs)[4], float (&s1)[4], float (&s2)[4]) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float s1 = (float)(sums[c + u] * inv_r), s2 = (float)(sums[p.C + c + u] * inv_r);
-      const float g = gamma ? __ldg(gamma + c + u) : 1.f;
-      o[u] = g * __ldg(p.rstd + c + u) * (m[u] - s1 - yh[u] * s2);
+      gs[u] = (gamma ? __ldg(gamma + c + u) : 1.f) * __ldg(p.rstd + c + u);
+      s1[u] = (float)(sums[c + u] * inv_r);
+      s2[u] = (float)(sums[p.C + c + u] * inv_r);
     }
-    *reinterpret_cast<float4*>(dy + r * ld_dy + c) = make_float4(o[0], o[1], o[2], o[3]);
+  };
+  if (TO_THREADS % tpr == 0) {
+    // a thread keeps its 4 channels over all its rows: every per-channel term is loaded once
+    const int c = (threadIdx.x % tpr) * 4;
+    const int rpp = TO_THREADS / tpr;                       // rows per CTA and pass
+    const BnChan ch = bn_chan(p, c);
+    float gs[4], s1[4], s2[4];
+    coefficients(c, gs, s1, s2);
+#pragma unroll 4
+    for (long long r = (long long)blockIdx.x * rpp + threadIdx.x / tpr; r < p.R; r += (long long)gridDim.x * rpp) {
+      float m[4], yh[4];
+      bn_bwd_m(p, ch, r, c, m, yh);
+      *reinterpret_cast<float4*>(dy + r * ld_dy + c) =
+          make_float4(gs[0] * (m[0] - s1[0] - yh[0] * s2[0]), gs[1] * (m[1] - s1[1] - yh[1] * s2[1]),
+                      gs[2] * (m[2] - s1[2] - yh[2] * s2[2]), gs[3] * (m[3] - s1[3] - yh[3] * s2[3]));
+    }
+    return;
+  }
+  const long long total = p.R * tpr;
+  for (long long e = (long long)blockIdx.x * TO_THREADS + threadIdx.x; e < total; e += (long long)gridDim.x * TO_THREADS) {
+    const long long r = e / tpr;
+    const int c = (int)(e - r * tpr) * 4;
+    const BnChan ch = bn_chan(p, c);
+    float m[4], yh[4], gs[4], s1[4], s2[4];
+    coefficients(c, gs, s1, s2);
+    bn_bwd_m(p, ch, r, c, m, yh);
+    *reinterpret_cast<float4*>(dy + r * ld_dy + c) =
+        make_float4(gs[0] * (m[0] - s1[0] - yh[0] * s2[0]), gs[1] * (m[1] - s1[1] - yh[1] * s2[1]),
+                    gs[2] * (m[2] - s1[2] - yh[2] * s2[2]), gs[3] * (m[3] - s1[3] - yh[3] * s2[3]));
   }
 }
 
@@ -283,11 +330,11 @@ extern "C" int ptt_linear_fwd_stats(const float* x, int ldx, long long R, int K,
 }
 
 extern "C" int ptt_linear_wgrad(const float* dy, int ldy, const float* x, int ldx, const float* x_ka, const float* x_kb,
-                                long long R, int M, int N, float* dw, int ldw, ptt_stream_t stream) {
+                                long long R, int M, int N, float* dw, int ldw, float* dbias_or_null, ptt_stream_t stream) {
   PTT_CHECK_ARG(R >= 0 && M >= 1 && N >= 1 && ldy >= M && ldx >= N && ldw >= N && ((x_ka == nullptr) == (x_kb == nullptr)));
   if (R == 0) return PTT_OK;
   PTT_CHECK_ARG(dy && x && dw);
-  return ptt_tc_wgrad_launch(dy, ldy, x, ldx, x_ka, x_kb, R, M, N, dw, ldw, as_stream(stream));
+  return ptt_tc_wgrad_launch(dy, ldy, x, ldx, x_ka, x_kb, R, M, N, dw, ldw, dbias_or_null, as_stream(stream));
 }
 
 extern "C" int ptt_col_stats(const float* y, int ldy, long long R, int C, double* sums, ptt_stream_t stream) {
@@ -297,7 +344,7 @@ extern "C" int ptt_col_stats(const float* y, int ldy, long long R, int C, double
   if (e != cudaSuccess) return (int)e;
   if (R == 0) return PTT_OK;
   PTT_CHECK_ARG(y != nullptr);
-  col_stats_kernel<<<grid_rows(R, 512), TO_THREADS, 0, st>>>(y, ldy, R, C, sums); PTT_LAUNCHED();
+  col_stats_kernel<<<grid_rows(R, 64), TO_THREADS, 0, st>>>(y, ldy, R, C, sums); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
@@ -313,11 +360,11 @@ extern "C" int ptt_bn_train_finalize(const double* sums, long long R, int C, con
 extern "C" int ptt_sa_group_rows(const float* xyz, const float* feats, int ldf, const float* new_xyz, const int* idx, int B,
                                  int N, int M, int ns, int C, float radius, int normalize_xyz, float* rows_out, int ld,
                                  ptt_stream_t stream) {
-  PTT_CHECK_ARG(B >= 0 && N >= 1 && M >= 0 && ns >= 1 && C >= 0 && ld >= C + 3 && (C == 0 || ldf >= C));
+  PTT_CHECK_ARG(B >= 0 && N >= 1 && M >= 0 && ns >= 1 && C >= 0 && ld >= C + 3 && ld % 4 == 0 && (C == 0 || ldf >= C));
   const long long rows = (long long)B * M * ns;
   if (rows == 0) return PTT_OK;
   PTT_CHECK_ARG(xyz && new_xyz && idx && rows_out && (C == 0 || feats));
-  sa_group_rows_kernel2<<<grid_rows(rows, 8), TO_THREADS, 0, as_stream(stream)>>>(xyz, feats, ldf, new_xyz, idx, N, M, ns, C, radius,
+  sa_group_rows_kernel2<<<grid_rows(rows * (ld / 4), TO_THREADS), TO_THREADS, 0, as_stream(stream)>>>(xyz, feats, ldf, new_xyz, idx, N, M, ns, C, radius,
                                                                                  normalize_xyz, rows, rows_out, ld); PTT_LAUNCHED();
   return ptt_launch_status();
 }
@@ -358,7 +405,7 @@ extern "C" int ptt_bn_relu_bwd(const float* dz, int ldz, const int* argmax_or_nu
   BnBwd p;
   p.dz = dz; p.ldz = ldz; p.arg = argmax_or_null; p.ns = ns; p.y = y; p.ldy = ldy;
   p.ka = ka; p.kb = kb; p.mean = mean; p.rstd = rstd; p.R = R; p.C = C;
-  bn_relu_bwd_reduce_kernel<<<grid_rows(R, 512), TO_THREADS, 0, st>>>(p, sums); PTT_LAUNCHED();
+  bn_relu_bwd_reduce_kernel<<<grid_rows(R, 64), TO_THREADS, 0, st>>>(p, sums); PTT_LAUNCHED();
   bn_relu_bwd_apply_kernel<<<grid_rows(R * (C / 4), TO_THREADS), TO_THREADS, 0, st>>>(p, sums, gamma, dy, ld_dy); PTT_LAUNCHED();
   return ptt_launch_status();
 }

@@ -25,8 +25,9 @@ def _pad4(c):
     return (int(c) + 3) // 4 * 4
 
 
-def linear_wgrad(dy, x, M, N, x_affine=None):
-    """dW (M, N) = dy[:, :M]^T . f(x[:, :N]), f = identity or relu(ka * x + kb) (ptt_linear_wgrad)."""
+def linear_wgrad(dy, x, M, N, x_affine=None, want_bias=False):
+    """dW (M, N) = dy[:, :M]^T . f(x[:, :N]), f = identity or relu(ka * x + kb) (ptt_linear_wgrad).
+    want_bias: -> (dW, db), db (M,) = the column sums of dy, accumulated by the same kernel."""
     _req(dy, _F, 2, "dy"), _req(x, _F, 2, "x")
     R = dy.shape[0]
     if x.shape[0] != R or dy.shape[1] < M or x.shape[1] < N:
@@ -34,10 +35,12 @@ def linear_wgrad(dy, x, M, N, x_affine=None):
     ka, kb = x_affine if x_affine is not None else (None, None)
     ldw = _pad4(N)
     with _DeviceGuard(dy.device):
-        dw = torch.zeros(M, ldw, dtype=_F, device=dy.device)
+        buf = torch.zeros(M * ldw + (M if want_bias else 0), dtype=_F, device=dy.device)   # one fill for both results
+        dw = buf[:M * ldw].view(M, ldw)
+        db = buf[M * ldw:] if want_bias else None
         check(_lib.lib().ptt_linear_wgrad(_ptr(dy), dy.shape[1], _ptr(x), x.shape[1], _ptr(ka), _ptr(kb), R, int(M), int(N),
-                                          _ptr(dw), ldw, _stream()), "ptt_linear_wgrad")
-    return dw[:, :N]
+                                          _ptr(dw), ldw, _ptr(db), _stream()), "ptt_linear_wgrad")
+    return (dw[:, :N], db) if want_bias else dw[:, :N]
 
 
 def col_stats(y, C):
@@ -192,9 +195,6 @@ def sa_train(xyz, feats_cm, new_xyz, idx, radius, normalize, mlp_module):
 # ------------------------------------------------------------------------------------------------
 # kNN vector-attention block (transformer_block/variants.py:127-165) in train() mode
 # ------------------------------------------------------------------------------------------------
-def _colsum(y, C):
-    return col_stats(y, C)[0].float()
-
 
 def _tr_layout(B, n, k, dp, dm):
     out = (ctypes.c_size_t * 7)()
@@ -251,20 +251,17 @@ class _TransformerTrain(torch.autograd.Function):
                   "ptt_tr_pair_inputs")
             grads = {}
             # out = fc2(res) + features
-            grads["fc2.weight"] = linear_wgrad(dout2, res, dp, dm)
-            grads["fc2.bias"] = _colsum(dout2, dp)
+            grads["fc2.weight"], grads["fc2.bias"] = linear_wgrad(dout2, res, dp, dm, want_bias=True)
             dres = lin_t(W["fc2.weight"])(dout2)
             dlogit = torch.empty(pairs, ld, dtype=_F, device=xyz.device)
             dvp = torch.empty(pairs, ld, dtype=_F, device=xyz.device)
             check(L.ptt_tr_softmax_bwd(_ptr(dres), dm, _ptr(attn), _ptr(vp), ld, tokens, k, dm, float(dm) ** 0.5, _ptr(dlogit),
                                        _ptr(dvp), _stream()), "ptt_tr_softmax_bwd")
             # logits = fc_gamma.2(g), g = relu(fc_gamma.0(a_in))
-            grads["fc_gamma.2.weight"] = linear_wgrad(dlogit, g, dm, dm)
-            grads["fc_gamma.2.bias"] = _colsum(dlogit, dm)
+            grads["fc_gamma.2.weight"], grads["fc_gamma.2.bias"] = linear_wgrad(dlogit, g, dm, dm, want_bias=True)
             dpre = lin_t(W["fc_gamma.2.weight"])(dlogit)
             check(L.ptt_tr_mask_positive(_ptr(dpre), _ptr(g), pairs * ld, _stream()), "ptt_tr_mask_positive")
-            grads["fc_gamma.0.weight"] = linear_wgrad(dpre, a_in, dm, dm)
-            grads["fc_gamma.0.bias"] = _colsum(dpre, dm)
+            grads["fc_gamma.0.weight"], grads["fc_gamma.0.bias"] = linear_wgrad(dpre, a_in, dm, dm, want_bias=True)
             da = lin_t(W["fc_gamma.0.weight"])(dpre)
             # a_in = q_i - k_j + pos_ij ; vp = v_j + pos_ij
             dq = torch.empty(tokens, dm, dtype=_F, device=xyz.device)
@@ -274,12 +271,10 @@ class _TransformerTrain(torch.autograd.Function):
                   "ptt_tr_pair_scatter")
             dpos = da
             # pos = fc_delta.2(h1), h1 = relu(fc_delta.0(delta))
-            grads["fc_delta.2.weight"] = linear_wgrad(dpos, h1, dm, dm)
-            grads["fc_delta.2.bias"] = _colsum(dpos, dm)
+            grads["fc_delta.2.weight"], grads["fc_delta.2.bias"] = linear_wgrad(dpos, h1, dm, dm, want_bias=True)
             dh1 = lin_t(W["fc_delta.2.weight"])(dpos)
             check(L.ptt_tr_mask_positive(_ptr(dh1), _ptr(h1), pairs * ld, _stream()), "ptt_tr_mask_positive")
-            grads["fc_delta.0.weight"] = linear_wgrad(dh1, delta, dm, 3)
-            grads["fc_delta.0.bias"] = _colsum(dh1, dm)
+            grads["fc_delta.0.weight"], grads["fc_delta.0.bias"] = linear_wgrad(dh1, delta, dm, 3, want_bias=True)
             # q, k, v = W x ; x = fc1(features)
             grads["w_qs.weight"] = linear_wgrad(dq, x, dm, dm)
             grads["w_ks.weight"] = linear_wgrad(dk, x, dm, dm)
@@ -287,8 +282,7 @@ class _TransformerTrain(torch.autograd.Function):
             dx = lin_t(W["w_qs.weight"])(dq)
             dx = lin_t(W["w_ks.weight"])(dk, residual=dx)
             dx = lin_t(W["w_vs.weight"])(dv, residual=dx)
-            grads["fc1.weight"] = linear_wgrad(dx, f2, dm, dp)
-            grads["fc1.bias"] = _colsum(dx, dm)
+            grads["fc1.weight"], grads["fc1.bias"] = linear_wgrad(dx, f2, dm, dp, want_bias=True)
             df = lin_t(W["fc1.weight"])(dx, residual=dout2)
         return (None, df.view(B, n, dp), None, *[grads[key].contiguous() for key in ops.TRANSFORMER_KEYS])
 

@@ -53,8 +53,10 @@ def test_linear_wgrad_vs_torch(R, M, N):
     ka = torch.from_numpy(rs.uniform(0.5, 1.5, N).astype(np.float32)).to(DEV)
     kb = torch.from_numpy(rs.normal(0, 0.5, N).astype(np.float32)).to(DEV)
     want = dy[:, :M].double().t() @ torch.relu(x[:, :N] * ka + kb).double()
-    got = train_ops.linear_wgrad(dy, x, M, N, (ka, kb))
+    got, db = train_ops.linear_wgrad(dy, x, M, N, (ka, kb), want_bias=True)
     close(got, want, 2e-5, "affine + relu on load")
+    assert db.shape == (M,)
+    close(db, dy[:, :M].double().sum(0), 2e-5, "bias gradient (column sums of dy) from the same kernel")
 
 
 def test_linear_fwd_operand_transform_and_padding():

@@ -31,3 +31,13 @@ for (r, m, n) in ((393216,256,128),(393216,128,128),(98304,512,512),(786432,64,6
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)/5
     print("  tc_gemm R=%d K=%d N=%d: %.1f us %.1f TFLOP/s(alg) traffic %.0f GB/s" % (r, m, n, ms*1e3, 2.0*r*m*n/ms/1e9, r*(m+n)*4/ms/1e6))
+    # BatchNorm + ReLU backward over the same rows (dense form): reads dz, y; writes dy
+    dz = torch.randn(r, m, device="cuda")
+    ka_, kb_ = torch.rand(m, device="cuda") + .5, torch.randn(m, device="cuda")
+    mean, rstd, gamma = torch.randn(m, device="cuda"), torch.rand(m, device="cuda") + .5, torch.rand(m, device="cuda") + .5
+    T.bn_relu_bwd(dz, None, 1, y, m, ka_, kb_, mean, rstd, gamma); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5): T.bn_relu_bwd(dz, None, 1, y, m, ka_, kb_, mean, rstd, gamma)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)/5
+    print("  bn_relu_bwd (reduce + apply) R=%d C=%d: %.1f us  %.0f GB/s (5 tensor passes)" % (r, m, ms*1e3, 5.0*r*m*4/ms/1e6))
