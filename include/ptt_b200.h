@@ -186,6 +186,10 @@ PTT_API int ptt_knn(const float* xyz, int B, int n, int k, int* knn_idx, ptt_str
 PTT_API size_t ptt_linear_params_floats(int K, int Cout);
 PTT_API int ptt_linear_pack(const float* weight, const float* bias, int K, int Cout, float* params,
                     ptt_stream_t stream);
+/* The same image from a STRIDED source: W[c, k] = weight[c * ld_c + k * ld_k] (ptt_linear_pack is ld_c = K, ld_k = 1; the
+ * transposed weight of an input-gradient contraction is ld_c = 1, ld_k = its row length -- no transposed copy). */
+PTT_API int ptt_linear_pack_strided(const float* weight, long long ld_c, long long ld_k, const float* bias, int K, int Cout,
+                            float* params, ptt_stream_t stream);
 PTT_API int ptt_linear_fwd(const float* x, int ldx, int R, int K, const float* params, int Cout, int relu,
                    const float* residual, int ldr, float* y, int ldy, ptt_stream_t stream);
 
@@ -289,10 +293,11 @@ PTT_API int ptt_sa_group_rows_grad(const float* d_rows, int ld, const int* idx, 
 PTT_API int ptt_bn_relu_maxpool(const float* y, int ldy, long long groups, int ns, int C, const float* ka, const float* kb,
                         float* out, int ldo, int* argmax, ptt_stream_t stream);
 /* Backward of y -> relu(BatchNorm_train(y)) [-> max over ns when argmax is given, dz then (R/ns, ldz)]:
- * dy (R,ld_dy) = gamma*rstd*(m - s1/R - yhat*s2/R), m = dz*[ka*y+kb > 0]; sums (2,C) double <- (s1 = d beta, s2 = d gamma). */
+ * dy (R,ld_dy) = gamma*rstd*(m - s1/R - yhat*s2/R), m = dz*[ka*y+kb > 0]; sums (2,C) double <- (s1 = d beta, s2 = d gamma);
+ * dparam_or_null (2,C) float <- the same two rows in fp32 (the parameter gradients, no conversion pass). */
 PTT_API int ptt_bn_relu_bwd(const float* dz, int ldz, const int* argmax_or_null, int ns, const float* y, int ldy, long long R,
                     int C, const float* ka, const float* kb, const float* mean, const float* rstd, const float* gamma,
-                    double* sums, float* dy, int ld_dy, ptt_stream_t stream);
+                    double* sums, float* dy, int ld_dy, float* dparam_or_null, ptt_stream_t stream);
 
 /* Training of the kNN vector-attention block (variants.py:149-165): the forward is ptt_transformer_block_fwd with attn
  * requested; these are the element kernels of its backward (ptt_b200/train_ops.py::_TransformerTrain), between the

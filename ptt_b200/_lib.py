@@ -47,6 +47,7 @@ SIGNATURES = {
     "ptt_knn": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "ptt_linear_params_floats": (c_size_t, [c_int, c_int]),
     "ptt_linear_pack": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "ptt_linear_pack_strided": (c_int, [_P, ctypes.c_longlong, ctypes.c_longlong, _P, c_int, c_int, _P, _P]),
     "ptt_linear_fwd": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, _P]),
     "ptt_transformer_params_floats": (c_size_t, [c_int, c_int]),
     "ptt_transformer_pack_params": (c_int, [c_int, c_int] + [_P] * 15 + [_P, _P]),
@@ -70,7 +71,7 @@ SIGNATURES = {
     "ptt_sa_group_rows": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_int, _P]),
     "ptt_sa_group_rows_grad": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_int, _P, _P, _P]),
     "ptt_bn_relu_maxpool": (c_int, [_P, c_int, ctypes.c_longlong, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
-    "ptt_bn_relu_bwd": (c_int, [_P, c_int, _P, c_int, _P, c_int, ctypes.c_longlong, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
+    "ptt_bn_relu_bwd": (c_int, [_P, c_int, _P, c_int, _P, c_int, ctypes.c_longlong, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
     "ptt_transformer_block_workspace_layout": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
     "ptt_tr_softmax_bwd": (c_int, [_P, c_int, _P, _P, c_int, ctypes.c_longlong, c_int, c_int, c_float, _P, _P, _P]),
     "ptt_tr_pair_inputs": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P]),

@@ -44,6 +44,9 @@ size_t ptt_tc_weight_halves(int K, int Cout);   // size of the fp16 image, in 2-
 // row_scale (optional, Cout floats): the image holds diag(row_scale) . W
 int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout, int K, void* img, cudaStream_t st,
                        const float* row_scale = nullptr, int batch = 1, long long w_bstride = 0, size_t img_bstride = 0);
+// nn.Linear image of ptt_linear_pack (transposed fp32 weight, bias row, fp16 image) from a strided source, one launch
+int ptt_linear_pack_all(const float* w, long long ld_c, long long ld_k, const float* bias, int K, int Cout, float* params,
+                        cudaStream_t st);
 bool ptt_tc_gemm_supported(const PttGemmArgs& a);
 int ptt_tc_gemm_launch(const PttGemmArgs& a, const void* wimg, cudaStream_t st);
 // floats occupied by the tcgen05 image of a (Cout, K) weight

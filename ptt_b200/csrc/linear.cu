@@ -153,12 +153,7 @@ int ptt_linear_pack_cols(const float* weight, const float* bias, int K, int Cout
 }
 
 int ptt_linear_pack_launch(const float* weight, const float* bias, int K, int Cout, float* params, cudaStream_t st) {
-  const int ldw = ptt_linear_ldw(Cout);
-  cudaError_t e = cudaMemsetAsync(params, 0, (size_t)(K + 1) * ldw * sizeof(float), st);
-  if (e != cudaSuccess) return (int)e;
-  int rc = ptt_linear_pack_cols(weight, bias, K, Cout, ldw, 0, params, st);
-  if (rc != PTT_OK) return rc;
-  return ptt_tc_pack_weight(weight, K, 1, Cout, K, params + (size_t)(K + 1) * ldw, st);
+  return ptt_linear_pack_all(weight, K, 1, bias, K, Cout, params, st);
 }
 
 extern "C" size_t ptt_linear_params_floats(int K, int Cout) {
@@ -170,6 +165,12 @@ extern "C" int ptt_linear_pack(const float* weight, const float* bias, int K, in
                                ptt_stream_t stream) {
   PTT_CHECK_ARG(K >= 1 && Cout >= 1 && weight && params);
   return ptt_linear_pack_launch(weight, bias, K, Cout, params, as_stream(stream));
+}
+
+extern "C" int ptt_linear_pack_strided(const float* weight, long long ld_c, long long ld_k, const float* bias, int K, int Cout,
+                                       float* params, ptt_stream_t stream) {
+  PTT_CHECK_ARG(K >= 1 && Cout >= 1 && weight && params);
+  return ptt_linear_pack_all(weight, ld_c, ld_k, bias, K, Cout, params, as_stream(stream));
 }
 
 extern "C" int ptt_linear_fwd(const float* x, int ldx, int R, int K, const float* params, int Cout, int relu,

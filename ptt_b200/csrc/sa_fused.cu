@@ -461,9 +461,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);
-              tc::mma_f16_w(d, da_hi + adv, db_hi + adv, IDESC2, (kb | k) != 0);
+              tc::mma_f16_w_fill(d, da_hi + adv, db_hi + adv, IDESC2, (kb | k) != 0);   // A_hi stays in the collector ...
+              tc::mma_f16_w_lastuse(d, da_hi + adv, db_lo + adv, IDESC2, 1);           // ... for the second MMA
               tc::mma_f16_w(d, da_lo + adv, db_hi + adv, IDESC2, 1);
-              tc::mma_f16_w(d, da_hi + adv, db_lo + adv, IDESC2, 1);
             }
             tc::mma_commit_w(&empty[stage]);
             if (++stage == SF_NS) { stage = 0; phase ^= 1; }
@@ -495,9 +495,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sa_fused_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);
-              tc::mma_f16_w(d, da_hi + adv, db_hi + adv, IDESC3, (kb | k) != 0);
+              tc::mma_f16_w_fill(d, da_hi + adv, db_hi + adv, IDESC3, (kb | k) != 0);   // A_hi stays in the collector ...
+              tc::mma_f16_w_lastuse(d, da_hi + adv, db_lo + adv, IDESC3, 1);           // ... for the second MMA
               tc::mma_f16_w(d, da_lo + adv, db_hi + adv, IDESC3, 1);
-              tc::mma_f16_w(d, da_hi + adv, db_lo + adv, IDESC3, 1);
             }
             tc::mma_commit_w(&empty[stage]);
             if (++stage == SF_NS) { stage = 0; phase ^= 1; }

@@ -25,6 +25,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // One arrival per WARP: every lane has finished (and fenced) its part, lane 0 signals for all 32 (the barrier is initialised
 // with the number of warps).  An mbarrier arrival is a serialised shared-memory atomic: 256 or 512 per-thread arrivals per
 // pipeline stage cost more than the stage's MMAs (measured on tc_wgrad: 1.2 us per 64-row k-block with nothing else to do).
+// Kernels whose stage is large (tc_gemm, ws_gemm: 128 rows per arrival round, 256 threads) measured 5-10 % SLOWER with the
+// extra __syncwarp and keep per-thread arrivals; sa_fused / tr_fused are neutral.
 __device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
@@ -195,6 +197,45 @@ __device__ __forceinline__ void mma_f16_2cta_w(uint32_t d_tmem, uint64_t desc_a,
       "elect.sync _|e, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Collector variants: the tensor core keeps the A operand of a `fill` MMA in its collector buffer and the next MMA, issued
+// with `lastuse`, takes it from there instead of reading shared memory again (SASS: gdesc.A_KEEP / gdesc.A_REUSE).  The
+// hi/lo split issues two consecutive MMAs with the same A (A_hi . B_hi, A_hi . B_lo): one operand read in six is saved.
+__device__ __forceinline__ void mma_f16_w_fill(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_w_lastuse(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_2cta_w_fill(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_2cta_w_lastuse(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }

@@ -58,8 +58,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   float* s_shift = reinterpret_cast<float*>(ctrl + 2048);          // [BN] epilogue shift
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * TBM;
-  const int ntile = blockIdx.y;
+  // blockIdx.x = row tile * n_tiles + column tile: the CTAs that read the same 128 rows of x are neighbours in launch order
+  // and share them through L2 (row tile fastest put them a whole wave apart: x came from HBM once per column tile)
+  const int n_tiles = (p.g.N + BN - 1) / BN;
+  const int ntile = blockIdx.x % n_tiles;
+  const int row0 = (blockIdx.x / n_tiles) * TBM;
   const PttGemmArgs& g = p.g;
   const int KB = p.k_blocks;
   const int bz = blockIdx.z;                                       // batch element
@@ -73,13 +76,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     s_row[tid] = r < g.R ? (g.a_rows ? g.a_rows[r] : r) : -1;
   }
   for (int c = tid; c < BN; c += TC_THREADS) {
-    const int col = blockIdx.y * BN + c;
+    const int col = ntile * BN + c;
     s_scale[c] = (g.scale && col < g.N) ? __ldg(g.scale + col) : 1.f;
     s_shift[c] = (g.shift && col < g.N) ? __ldg(g.shift + col) : 0.f;
   }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(&full_a[s], 8);
+      tc::mbar_init(&full_a[s], 256);
       tc::mbar_init(&full_b[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         *reinterpret_cast<uint2*>(a_lo + off) = pl;
       }
       tc::fence_proxy_async_smem();
-      tc::mbar_arrive_warp(&full_a[stage]);
+      tc::mbar_arrive(&full_a[stage]);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
@@ -288,11 +291,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 //   block (nb, kb, half) at ((nb * KB + kb) * 2 + half) * 8 KB; inside, row r (0..63) / 16-byte chunk c at
 //   sw128_offset(r, c); rows >= Cout and k >= K are zero.
 //   src(c, k) = w[c * ld_c + k * ld_k]   (so a transposed (K, ldw) image can be the source too)
+// wt (optional, batch 1 only): the CUDA-core image of the same layer is written by the same launch -- wt[k * ldw + c] =
+// src(c, k) for k < K, the bias row at k = K, zeros in the padding columns (one launch per layer instead of memset + two)
 __global__ void tc_pack_weight_kernel(const float* __restrict__ w, long long ld_c, long long ld_k, int Cout, int K, int NB,
                                       int KB, const float* __restrict__ row_scale, __half* __restrict__ img,
-                                      long long w_bstride, size_t img_bstride) {
+                                      long long w_bstride, size_t img_bstride, float* __restrict__ wt, int ldw,
+                                      const float* __restrict__ bias) {
   w += (long long)blockIdx.y * w_bstride;                                                  // batch element
   img = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(img) + (size_t)blockIdx.y * img_bstride);
+  if (wt != nullptr) {
+    const int total_t = (K + 1) * ldw;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total_t; e += gridDim.x * blockDim.x) {
+      const int k = e / ldw, c = e - k * ldw;
+      wt[e] = c < Cout ? (k < K ? w[(long long)c * ld_c + (long long)k * ld_k] : (bias ? bias[c] : 0.f)) : 0.f;
+    }
+  }
   const long long total = (long long)NB * KB * 64 * 8;   // (block, row, chunk)
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(e & 7);
@@ -326,7 +339,7 @@ int tc_launch(const TcParams& p, cudaStream_t st) {
     if (int rc = tc::tc_bind_fault(ptt_fault_word())) return rc;
     configured[dev] = true;
   }
-  dim3 grid(ceil_div(p.g.R, TBM), ceil_div(p.g.N, BN), p.g.batch > 0 ? p.g.batch : 1);
+  dim3 grid(ceil_div(p.g.R, TBM) * ceil_div(p.g.N, BN), 1, p.g.batch > 0 ? p.g.batch : 1);
   kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p); PTT_LAUNCHED();
   return ptt_launch_status();
 }
@@ -343,7 +356,19 @@ int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout,
   const long long total = (long long)NB * KB * 512;
   dim3 grid((unsigned)llmin_((total + 255) / 256, 2048), batch > 0 ? batch : 1);
   tc_pack_weight_kernel<<<grid, 256, 0, st>>>(w, ld_c, ld_k, Cout, K, NB, KB, row_scale, static_cast<__half*>(img), w_bstride,
-                                              img_bstride); PTT_LAUNCHED();
+                                              img_bstride, nullptr, 0, nullptr); PTT_LAUNCHED();
+  return ptt_launch_status();
+}
+
+// the whole packed nn.Linear image (transposed fp32 weight + bias row + fp16 hi/lo image) in one launch
+int ptt_linear_pack_all(const float* w, long long ld_c, long long ld_k, const float* bias, int K, int Cout, float* params,
+                        cudaStream_t st) {
+  const int NB = ceil_div(Cout, 64), KB = ceil_div(K, 64), ldw = ptt_linear_ldw(Cout);
+  const long long total = (long long)NB * KB * 512;
+  dim3 grid((unsigned)llmin_((total + 255) / 256, 2048), 1);
+  tc_pack_weight_kernel<<<grid, 256, 0, st>>>(w, ld_c, ld_k, Cout, K, NB, KB, nullptr,
+                                              reinterpret_cast<__half*>(params + (size_t)(K + 1) * ldw), 0, 0, params, ldw, bias);
+  PTT_LAUNCHED();
   return ptt_launch_status();
 }
 

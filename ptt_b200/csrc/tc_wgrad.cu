@@ -10,7 +10,7 @@
 // a_major / b_major bits tell the tensor core to read them transposed.  No transposition pass, no scattered 2-byte
 // stores.  fp32-class accuracy through the same fp16 hi/lo split as tc_gemm.cu (three MMAs per K = 16 step).
 //
-// Grid: (row chunks [split-K], 128-channel tiles of M, tiles of N).  A CTA reduces ITS rows into a TMEM accumulator
+// Grid: ((M tile, N tile) pairs, row chunks [split-K]).  A CTA reduces ITS rows into a TMEM accumulator
 // (128 lanes x NT*64 columns) and adds it to dW with fp32 atomics (the order of those additions is not fixed, like the
 // atomicAdd scatter of upstream's group_points_grad; the differences are ~1e-7 relative).
 //   warps 0-15 producers: fp32 rows of dY and X -> (optional per-channel affine + ReLU on X) -> fp16 hi/lo -> smem;
@@ -35,6 +35,7 @@ struct WgArgs {
   long long R;
   int M, N;
   long long rows_per_cta;                // multiple of the k-block height
+  int tiles_m;
   int vec4;                              // dw rows are 16-byte aligned and ldw % 4 == 0: vector reductions
 };
 
@@ -81,9 +82,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long r_begin = (long long)blockIdx.x * a.rows_per_cta;
+  // blockIdx.x = the (M tile, N tile) pair, blockIdx.y = the row chunk: the CTAs that read the SAME rows are neighbours in
+  // launch order, run at the same time and share those rows through L2 (with the row chunk fastest, the re-reads of a
+  // 512 x 512 layer -- dY twice, X four times -- came from HBM: 1.2 GB instead of 0.4 GB)
+  const int tile_m = blockIdx.x % a.tiles_m, tile_n = blockIdx.x / a.tiles_m;
+  const long long r_begin = (long long)blockIdx.y * a.rows_per_cta;
   const long long r_end = r_begin + a.rows_per_cta < a.R ? r_begin + a.rows_per_cta : a.R;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.z * BN;
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
   const int KB = r_end > r_begin ? (int)((r_end - r_begin + KBR - 1) / KBR) : 0;
 
   if (tid == 0) {
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         }
       }
     }
-    if (a.dbias != nullptr && blockIdx.z == 0) {          // rows beyond r_end and channels beyond M were staged as zeros
+    if (a.dbias != nullptr && tile_n == 0) {          // rows beyond r_end and channels beyond M were staged as zeros
       const int m = m0 + (tid % AQ) * 4;
       const float bs[4] = {bsum.x, bsum.y, bsum.z, bsum.w};
 #pragma unroll
@@ -309,7 +314,8 @@ int wg_launch(WgArgs a, int ntiles_n, cudaStream_t st) {
   if (nsplit < 1) nsplit = 1;
   a.rows_per_cta = ((kblocks + nsplit - 1) / nsplit) * KBR;
   nsplit = (int)((a.R + a.rows_per_cta - 1) / a.rows_per_cta);
-  dim3 grid(nsplit, tiles_m, ntiles_n);
+  a.tiles_m = tiles_m;
+  dim3 grid(tiles_mn, nsplit);
   kern<<<grid, WG_THREADS, Cfg::SMEM, st>>>(a); PTT_LAUNCHED();
   return ptt_launch_status();
 }

@@ -236,7 +236,9 @@ __global__ void __launch_bounds__(TO_THREADS) bn_relu_bwd_reduce_kernel(const Bn
 // dy = gamma * rstd * (m - s1 / R - yhat * s2 / R)
 __global__ void __launch_bounds__(TO_THREADS) bn_relu_bwd_apply_kernel(const BnBwd p, const double* __restrict__ sums,
                                                                         const float* __restrict__ gamma, float* __restrict__ dy,
-                                                                        int ld_dy) {
+                                                                        int ld_dy, float* __restrict__ dparam) {
+  if (dparam != nullptr && blockIdx.x == 0)                 // (2, C) fp32 copy of the sums: d beta, d gamma as the optimiser wants them
+    for (int c = threadIdx.x; c < 2 * p.C; c += TO_THREADS) dparam[c] = (float)sums[c];
   const int tpr = p.C / 4;                                  // threads per row
   const double inv_r = 1.0 / (double)p.R;
   auto coefficients = [&](int c, float (&gs)[4], float (&s1)[4], float (&s2)[4]) {
@@ -395,7 +397,8 @@ extern "C" int ptt_bn_relu_maxpool(const float* y, int ldy, long long groups, in
 
 extern "C" int ptt_bn_relu_bwd(const float* dz, int ldz, const int* argmax_or_null, int ns, const float* y, int ldy, long long R,
                                int C, const float* ka, const float* kb, const float* mean, const float* rstd,
-                               const float* gamma, double* sums, float* dy, int ld_dy, ptt_stream_t stream) {
+                               const float* gamma, double* sums, float* dy, int ld_dy, float* dparam_or_null,
+                               ptt_stream_t stream) {
   PTT_CHECK_ARG(R >= 1 && C >= 4 && C % 4 == 0 && C <= 4 * TO_THREADS && ldy >= C && ldy % 4 == 0 && ldz >= C && ldz % 4 == 0 &&
                 ld_dy >= C && ld_dy % 4 == 0 && ns >= 1);
   PTT_CHECK_ARG(dz && y && ka && kb && mean && rstd && sums && dy);
@@ -406,6 +409,6 @@ extern "C" int ptt_bn_relu_bwd(const float* dz, int ldz, const int* argmax_or_nu
   p.dz = dz; p.ldz = ldz; p.arg = argmax_or_null; p.ns = ns; p.y = y; p.ldy = ldy;
   p.ka = ka; p.kb = kb; p.mean = mean; p.rstd = rstd; p.R = R; p.C = C;
   bn_relu_bwd_reduce_kernel<<<grid_rows(R, 64), TO_THREADS, 0, st>>>(p, sums); PTT_LAUNCHED();
-  bn_relu_bwd_apply_kernel<<<grid_rows(R * (C / 4), TO_THREADS), TO_THREADS, 0, st>>>(p, sums, gamma, dy, ld_dy); PTT_LAUNCHED();
+  bn_relu_bwd_apply_kernel<<<grid_rows(R * (C / 4), TO_THREADS), TO_THREADS, 0, st>>>(p, sums, gamma, dy, ld_dy, dparam_or_null); PTT_LAUNCHED();
   return ptt_launch_status();
 }

@@ -61,12 +61,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ws_gemm_kernel(const __grid_con
 
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
-      tc::mbar_init(&a_full[s], 8);
+      tc::mbar_init(&a_full[s], 256);
       tc::mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&d_full[s], 1);
-      tc::mbar_init(&d_free[s], 8);
+      tc::mbar_init(&d_free[s], 256);
     }
     tc::mbar_init(w_full, 1);
     tc::mbar_init_fence();
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ws_gemm_kernel(const __grid_con
           tc::tmem_ld32(lane_addr + (uint32_t)(buf * NCH * 128 + h * 128 + rhalf * 64 + b * 32), v);
           if (h == NCH - 1 && b == 1) {                         // accumulator drained
             tc::tc_fence_before();
-            tc::mbar_arrive_warp(&d_free[buf]);
+            tc::mbar_arrive(&d_free[buf]);
           }
           const long long rb = r0 + b * 32;
           if (rb >= a.R || !ch_ok) continue;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ws_gemm_kernel(const __grid_con
         *reinterpret_cast<uint2*>(a_lo + off) = pl;
       }
       tc::fence_proxy_async_smem();
-      tc::mbar_arrive_warp(&a_full[stage]);
+      tc::mbar_arrive(&a_full[stage]);
       if (++stage == nsa) { stage = 0; phase ^= 1; }
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];

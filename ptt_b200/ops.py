@@ -34,6 +34,19 @@ def _req(t, dtype, ndim, name):
     return t
 
 
+def _req_strided(t, dtype, ndim, name):
+    """_req without the contiguity requirement (the callee takes the strides)."""
+    if not isinstance(t, torch.Tensor):
+        raise PttError("%s must be a tensor" % name)
+    if not t.is_cuda:
+        raise PttError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != dtype:
+        raise PttError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if t.dim() != ndim:
+        raise PttError("%s must have %d dimensions, got shape %s" % (name, ndim, tuple(t.shape)))
+    return t
+
+
 def _same_device(*ts):
     dev = ts[0].device
     for t in ts[1:]:
@@ -282,7 +295,8 @@ class PackedLinear:
     """nn.Linear parameters in the library's packed layout (ptt_linear_pack)."""
 
     def __init__(self, weight, bias=None, check_range=True):
-        _req(weight, _F, 2, "weight")
+        """weight (Cout, K): any strides (a transposed view packs without a copy)."""
+        _req_strided(weight, _F, 2, "weight")
         self.cout, self.k = weight.shape
         self.has_bias = bias is not None
         if check_range:
@@ -295,13 +309,13 @@ class PackedLinear:
     def repack(self, weight, bias=None):
         """Pack new values of the same shape into the existing image (no allocation, no synchronisation, no range check:
         the training path repacks every step)."""
-        _req(weight, _F, 2, "weight")
+        _req_strided(weight, _F, 2, "weight")
         if tuple(weight.shape) != (self.cout, self.k):
             raise PttError("repack: weight must be (%d,%d)" % (self.cout, self.k))
         self.has_bias = bias is not None
         with _DeviceGuard(weight.device):
-            check(_lib.lib().ptt_linear_pack(_ptr(weight), _ptr(bias), self.k, self.cout, _ptr(self.params), _stream()),
-                  "ptt_linear_pack")
+            check(_lib.lib().ptt_linear_pack_strided(_ptr(weight), weight.stride(0), weight.stride(1), _ptr(bias), self.k, self.cout,
+                                                     _ptr(self.params), _stream()), "ptt_linear_pack_strided")
         return self
 
     def __call__(self, x, relu=False, residual=None, in_affine=None, ld_out=None):
@@ -335,9 +349,11 @@ class PackedLinear:
         return y
 
 
-def linear_with_stats(lin, x, in_affine=None, want_stats=True, ld_out=None):
+def linear_with_stats(lin, x, in_affine=None, want_stats=True, ld_out=None, zero_pad=True):
     """y = lin(f(x)) without activation / residual, plus (optionally) the column sums of y and y*y as a (2, Cout) float64
-    tensor (ptt_linear_fwd_stats: bias-free layers over many rows take the weight-stationary persistent kernel)."""
+    tensor (ptt_linear_fwd_stats: bias-free layers over many rows take the weight-stationary persistent kernel).
+    ld_out > Cout: rows are padded; zero_pad=False leaves the padding columns uninitialised (for consumers that never
+    read them -- it saves a fill pass over the whole result)."""
     _req(x, _F, 2, "x")
     R, ldx = x.shape
     if ldx < lin.k:
@@ -345,7 +361,7 @@ def linear_with_stats(lin, x, in_affine=None, want_stats=True, ld_out=None):
     ka, kb = in_affine if in_affine is not None else (None, None)
     ldy = lin.cout if ld_out is None else int(ld_out)
     with _DeviceGuard(x.device):
-        y = torch.empty(R, ldy, dtype=_F, device=x.device) if ldy == lin.cout else torch.zeros(R, ldy, dtype=_F, device=x.device)
+        y = (torch.empty if (ldy == lin.cout or not zero_pad) else torch.zeros)(R, ldy, dtype=_F, device=x.device)
         sums = torch.empty(2, lin.cout, dtype=torch.float64, device=x.device) if want_stats else None
         check(_lib.lib().ptt_linear_fwd_stats(_ptr(x), ldx, R, lin.k, _ptr(ka), _ptr(kb), _ptr(lin.params), lin.cout,
                                               int(lin.has_bias), _ptr(y), ldy, _ptr(sums), _stream()), "ptt_linear_fwd_stats")

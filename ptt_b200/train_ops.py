@@ -96,15 +96,16 @@ def bn_relu_maxpool(y, groups, ns, C, ka, kb):
 
 
 def bn_relu_bwd(dz, argmax, ns, y, C, ka, kb, mean, rstd, gamma):
-    """-> (dy (R, C), sums (2, C) float64 = (d beta, d gamma))."""
+    """-> (dy (R, C), sums (2, C) float64 = (d beta, d gamma), dparam (2, C) float32 = the same two rows)."""
     R = y.shape[0]
     with _DeviceGuard(y.device):
         dy = torch.empty(R, C, dtype=_F, device=y.device)
         sums = torch.empty(2, C, dtype=_F64, device=y.device)
+        dparam = torch.empty(2, C, dtype=_F, device=y.device)
         check(_lib.lib().ptt_bn_relu_bwd(_ptr(dz), dz.shape[1], _ptr(argmax), int(ns), _ptr(y), y.shape[1], R, int(C), _ptr(ka),
-                                         _ptr(kb), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(sums), _ptr(dy), C, _stream()),
-              "ptt_bn_relu_bwd")
-    return dy, sums
+                                         _ptr(kb), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(sums), _ptr(dy), C, _ptr(dparam),
+                                         _stream()), "ptt_bn_relu_bwd")
+    return dy, sums, dparam
 
 
 class _SATrain(torch.autograd.Function):
@@ -155,16 +156,17 @@ class _SATrain(torch.autograd.Function):
         pooled = arg
         for l in range(L - 1, -1, -1):
             cout, cin = ws[l].shape[0], ws[l].shape[1]
-            dy, sums = bn_relu_bwd(dz, pooled, ns, ys[l], cout, affs[l][0], affs[l][1], stats[l][0], stats[l][1], gs[l])
+            dy, _, dparam = bn_relu_bwd(dz, pooled, ns, ys[l], cout, affs[l][0], affs[l][1], stats[l][0], stats[l][1], gs[l])
             pooled = None
-            grads[5 * l + 1] = sums[1].float()                       # d gamma
-            grads[5 * l + 2] = sums[0].float()                       # d beta
+            grads[5 * l + 1] = dparam[1]                             # d gamma
+            grads[5 * l + 2] = dparam[0]                             # d beta
             src, aff = (x0, None) if l == 0 else (ys[l - 1], affs[l - 1])
             grads[5 * l] = linear_wgrad(dy, src, cout, cin, aff).reshape(ws[l].shape)
             need_dx = l > 0 or ctx.needs_input_grad[0] or (C > 0 and ctx.needs_input_grad[1]) or ctx.needs_input_grad[2]
             if need_dx:
-                wt = ops.PackedLinear(ws[l].reshape(cout, cin).t().contiguous(), None, check_range=False)
-                dz, _ = ops.linear_with_stats(wt, dy, want_stats=False, ld_out=_pad4(cin))
+                wt = ops.PackedLinear(ws[l].reshape(cout, cin).t(), None, check_range=False)   # strided pack: no transposed copy
+                # padded rows only below layer 0, where ptt_sa_group_rows_grad reads the first 3 + C columns and nothing else
+                dz, _ = ops.linear_with_stats(wt, dy, want_stats=False, ld_out=_pad4(cin), zero_pad=False)
         d_xyz = d_feats = d_new = None
         if ctx.needs_input_grad[0] or (C > 0 and ctx.needs_input_grad[1]) or ctx.needs_input_grad[2]:
             want_xyz = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
@@ -234,8 +236,8 @@ class _TransformerTrain(torch.autograd.Function):
         res = ws[off[3]: off[3] + tokens * ld].view(tokens, ld)
         g = ws[off[4]: off[4] + pairs * ld].view(pairs, ld)
         vp = ws[off[5]: off[5] + pairs * ld].view(pairs, ld)
-        lin = lambda w, b=None: ops.PackedLinear(w.contiguous(), b, check_range=False)
-        lin_t = lambda w: ops.PackedLinear(w.t().contiguous(), None, check_range=False)
+        lin = lambda w, b=None: ops.PackedLinear(w, b, check_range=False)
+        lin_t = lambda w: ops.PackedLinear(w.t(), None, check_range=False)      # strided pack: no transposed copy
         f2 = features.reshape(tokens, dp)
         dout2 = dout.reshape(tokens, dp).contiguous()
         # token-level projections, recomputed (tokens x d_model each)

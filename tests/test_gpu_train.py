@@ -59,6 +59,21 @@ def test_linear_wgrad_vs_torch(R, M, N):
     close(db, dy[:, :M].double().sum(0), 2e-5, "bias gradient (column sums of dy) from the same kernel")
 
 
+def test_packed_linear_from_a_transposed_view_needs_no_copy():
+    """ptt_linear_pack_strided: the input-gradient contraction packs W^T straight from the (Cout, K) parameter."""
+    rs = np.random.RandomState(5)
+    for cout, k in ((128, 131), (64, 6), (512, 512), (100, 36)):
+        w = torch.from_numpy(rs.standard_normal((cout, k)).astype(np.float32)).to(DEV)
+        a = ops.PackedLinear(w.t(), None)                 # (K, Cout) view with strides (1, K)
+        b = ops.PackedLinear(w.t().contiguous(), None)
+        assert not w.t().is_contiguous() and torch.equal(a.params, b.params)
+    bias = torch.from_numpy(rs.standard_normal(64).astype(np.float32)).to(DEV)
+    w = torch.from_numpy(rs.standard_normal((64, 20)).astype(np.float32)).to(DEV)
+    lin = ops.PackedLinear(w, bias)
+    ldw = 64
+    assert torch.equal(lin.params[:20 * ldw].view(20, ldw), w.t()) and torch.equal(lin.params[20 * ldw: 21 * ldw], bias)
+
+
 def test_linear_fwd_operand_transform_and_padding():
     rs = np.random.RandomState(3)
     for R, K, Cout in ((1000, 128, 256), (333, 64, 131), (129, 260, 256)):
@@ -95,7 +110,7 @@ def test_two_phase_batchnorm_and_pool_vs_torch():
         # backward through pool + relu + batch norm
         dout = torch.from_numpy(rs.standard_normal((groups, C)).astype(np.float32)).to(DEV)
         zt.max(1)[0].backward(dout)
-        dy, sums = train_ops.bn_relu_bwd(dout, arg, ns, y, C, ka, kb, mean, rstd, gamma)
+        dy, sums, _ = train_ops.bn_relu_bwd(dout, arg, ns, y, C, ka, kb, mean, rstd, gamma)
         close(dy, yt.grad, 1e-4, "dy (pooled)")
         # dense dz
         yt.grad = None
@@ -104,9 +119,10 @@ def test_two_phase_batchnorm_and_pool_vs_torch():
         bet = beta.clone().requires_grad_(True)
         z2 = torch.relu(F.batch_norm(yt.t().reshape(1, C, R), None, None, gam, bet, training=True, eps=1e-5))
         z2[0].t().backward(dz)
-        dy, sums = train_ops.bn_relu_bwd(dz, None, 1, y, C, ka, kb, mean, rstd, gamma)
+        dy, sums, dparam = train_ops.bn_relu_bwd(dz, None, 1, y, C, ka, kb, mean, rstd, gamma)
         close(dy, yt.grad, 1e-4, "dy (dense)")
         close(sums[1], gam.grad, 1e-4, "d gamma"), close(sums[0], bet.grad, 1e-4, "d beta")
+        assert dparam.dtype == torch.float32 and torch.equal(dparam, sums.float()), "fp32 parameter gradients = the rounded sums"
 
 
 def close_grad(a, b, what="", cos_tol=3e-4, l2_tol=2.5e-2):
