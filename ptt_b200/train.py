@@ -70,8 +70,13 @@ def time_train_step(device, world=1, rank=0, local_rank=0, batch=48, steps=5, wa
     net = HotPathNet()
     synth.load_filled(net, seed=0)
     net = net.to(device).train()
-    # small buckets: the 16.4 MB of gradients are all-reduced in ~4 MB pieces while the backward pass is still running
-    model = (nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], bucket_cap_mb=4, gradient_as_bucket_view=True)
+    # DDP as train_tracking.py:158-159 builds it, with three measured settings (2 GPUs: 18.8 -> 18.2 ms per step):
+    # 4 MB buckets (the 16.4 MB of gradients are all-reduced in pieces while the backward pass is still running),
+    # static_graph (same parameters every step), and no per-step buffer broadcast: the BatchNorm running statistics are
+    # per-GPU in the reference too (no --sync_bn), rank 0 -- whose buffers a checkpoint holds -- never receives anything,
+    # so the broadcast only overwrites the other ranks' copies and costs 0.5 ms per step.
+    model = (nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], bucket_cap_mb=4, gradient_as_bucket_view=True,
+                                                 broadcast_buffers=False, static_graph=True)
              if world > 1 else net)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.5, 0.999))
     n_params = sum(p.numel() for p in net.parameters())
