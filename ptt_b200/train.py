@@ -57,12 +57,23 @@ class HotPathNet(nn.Module):
         return {"search_feats": s_feat, "template_feats": t_feat, "centroid_feats": cen, "box_sa_feats": b_feat, "box_feats": box}
 
 
-def time_train_step(device, world=1, rank=0, local_rank=0, batch=48, steps=5, warmup=3, n_search=1024, n_template=512):
+def time_train_step(device, world=1, rank=0, local_rank=0, batch=48, steps=5, warmup=3, n_search=1024, n_template=512,
+                    graph=True):
     """One training step of the hot path the way the reference trains (tools/train_utils/train_utils.py:40-51,
     tools/train_tracking.py:158-159, ptt.yaml OPTIMIZATION): forward in train() mode (BatchNorm batch statistics), loss,
     backward, DistributedDataParallel gradient all-reduce over NCCL (the only collective; needs an initialised process
     group when world > 1), clip_grad_norm_(10), Adam(lr 1e-3, betas (0.5, 0.999)).  Every rank trains on its own `batch`
-    synthetic frames (weak scaling).  Timed on the device with CUDA events.  Returns a dict (ms_per_step of THIS rank)."""
+    synthetic frames (weak scaling).  Timed on the device with CUDA events.  Returns a dict (ms_per_step of THIS rank).
+
+    graph=True: after the eager warm-up the WHOLE step (forward, backward, the NCCL all-reduce DDP issues from its hooks,
+    clipping, Adam) is captured once into a CUDA graph and the timed steps are replays with fresh inputs copied into the
+    static input buffers.  The step is ~670 launches whose host side (autograd, wrappers, DDP bookkeeping) costs 14 ms
+    against 17 ms of kernels on an idle host and MORE than the kernels once 8 ranks share 16 cores; the replay has no host
+    side.  Set-up follows torch's rules for capturing a full backward under DDP (async error handling off before
+    init_process_group -- see `prepare_env_for_graphs` --, DDP built on a side stream, >= 11 eager iterations first).
+    graph=False, or a failed capture (reported in `launch_mode`), times eager steps."""
+    import time
+
     import torch.distributed as dist
 
     from . import synth
@@ -70,23 +81,26 @@ def time_train_step(device, world=1, rank=0, local_rank=0, batch=48, steps=5, wa
     net = HotPathNet()
     synth.load_filled(net, seed=0)
     net = net.to(device).train()
-    # DDP as train_tracking.py:158-159 builds it, with three measured settings (2 GPUs: 18.8 -> 18.2 ms per step):
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    # DDP as train_tracking.py:158-159 builds it, with three measured settings (2 GPUs: 18.8 -> 18.2 ms per eager step):
     # 4 MB buckets (the 16.4 MB of gradients are all-reduced in pieces while the backward pass is still running),
     # static_graph (same parameters every step), and no per-step buffer broadcast: the BatchNorm running statistics are
     # per-GPU in the reference too (no --sync_bn), rank 0 -- whose buffers a checkpoint holds -- never receives anything,
     # so the broadcast only overwrites the other ranks' copies and costs 0.5 ms per step.
-    model = (nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], bucket_cap_mb=4, gradient_as_bucket_view=True,
-                                                 broadcast_buffers=False, static_graph=True)
-             if world > 1 else net)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.5, 0.999))
+    with torch.cuda.stream(side):
+        model = (nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], bucket_cap_mb=4, gradient_as_bucket_view=True,
+                                                     broadcast_buffers=False, static_graph=True)
+                 if world > 1 else net)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.5, 0.999), capturable=bool(graph))
     n_params = sum(p.numel() for p in net.parameters())
     sets = [(torch.from_numpy(synth.make_clouds(batch, n_search, 3000 + 16 * rank + i, "dense")).to(device),
              torch.from_numpy(synth.make_clouds(batch, n_template, 4000 + 16 * rank + i, "dense", role="template")).to(device))
             for i in range(4)]
+    in_s, in_t = torch.empty_like(sets[0][0]), torch.empty_like(sets[0][1])      # static inputs of the captured step
 
-    def step(i):
-        s, t = sets[i % 4]
-        out = model(s, t)
+    def step():
+        out = model(in_s, in_t)
         loss = sum((v.float() ** 2).mean() for v in out.values())      # synthetic L2 loss on every block output
         opt.zero_grad(set_to_none=True)
         loss.backward()                                                   # DDP all-reduces the gradients in here
@@ -94,16 +108,71 @@ def time_train_step(device, world=1, rank=0, local_rank=0, batch=48, steps=5, wa
         opt.step()
         return loss
 
-    for i in range(warmup):
-        step(i)
+    def feed(i):
+        in_s.copy_(sets[i % 4][0])
+        in_t.copy_(sets[i % 4][1])
+
+    n_warm = max(warmup, 11 if (graph and world > 1) else 3)
+    with torch.cuda.stream(side):
+        for i in range(n_warm):
+            feed(i)
+            step()
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize(device)
+    mode, g, g_loss = "eager launches", None, None
+    if graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(g):
+                g_loss = step()
+            mode = "one CUDA graph per step (forward + backward + all-reduce + clip + Adam), replayed"
+        except Exception as e:                                            # noqa: BLE001 - report and time eager steps
+            g = None
+            torch.cuda.synchronize(device)
+            mode = "eager launches (graph capture failed: %s)" % (str(e).splitlines()[0][:120] if str(e) else type(e).__name__)
+
+    def run(i):
+        feed(i)
+        if g is not None:
+            g.replay()
+            return g_loss
+        return step()
+
+    for i in range(2):
+        run(i)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    losses = []
     e0.record()
-    losses = [step(i) for i in range(steps)]
+    t0 = time.perf_counter()
+    for i in range(steps):
+        losses.append(run(i).detach().clone())
+    host_ms = (time.perf_counter() - t0) * 1e3 / steps                  # host time to ENQUEUE a step (no synchronisation inside)
     e1.record()
     torch.cuda.synchronize(device)
-    return {"ms_per_step": e0.elapsed_time(e1) / steps, "steps": steps, "warmup": warmup, "batch_per_gpu": batch,
-            "parameters": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
-            "loss_first_last": [float(losses[0].detach()), float(losses[-1].detach())]}
+    in_sync = None
+    if world > 1:
+        # the DDP invariant after the timed steps: every rank holds bit-identical parameters (the all-reduce -- captured
+        # in the graph or not -- delivered the same averaged gradients everywhere)
+        digest = torch.stack([p.detach().double().sum() for p in net.parameters()] +
+                             [p.detach().double().abs().sum() for p in net.parameters()])
+        gathered = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(gathered, digest)
+        in_sync = all(bool(torch.equal(gathered[0], t)) for t in gathered[1:])
+    return {"ms_per_step": e0.elapsed_time(e1) / steps, "host_enqueue_ms_per_step": host_ms, "launch_mode": mode,
+            "ranks_hold_identical_parameters": in_sync, "steps": steps,
+            "warmup": n_warm, "batch_per_gpu": batch, "parameters": n_params,
+            "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
+            "loss_first_last": [float(losses[0]), float(losses[-1])]}
+
+
+def prepare_env_for_graphs():
+    """Call before torch.distributed.init_process_group: capturing NCCL collectives into a CUDA graph needs the process
+    group's asynchronous error handling (a watchdog that queries events of in-flight work) switched off."""
+    import os
+
+    os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+    os.environ.setdefault("NCCL_ASYNC_ERROR_HANDLING", "0")

@@ -237,6 +237,21 @@ def test_hot_path_net_train_step_native_vs_decomposition():
         close(ba[k], bb[k], 1e-4, k)
 
 
+def test_train_step_cuda_graph_replay_matches_eager_steps():
+    """train.time_train_step: the whole step (forward, backward, clipping, Adam) captured once and replayed must follow the
+    same loss trajectory as eager launches of the same step (the split-K atomics are the only unordered arithmetic)."""
+    from ptt_b200 import train
+    runs = {}
+    for graph in (True, False):
+        r = train.time_train_step(torch.device(DEV), batch=4, steps=4, warmup=3, graph=graph)
+        runs[graph] = r
+        assert ("CUDA graph" in r["launch_mode"]) == graph, r["launch_mode"]
+    a, b = runs[True]["loss_first_last"], runs[False]["loss_first_last"]
+    assert all(np.isfinite(a)) and a[1] < a[0], "the loss goes down"
+    assert abs(a[0] - b[0]) <= 2e-3 * abs(b[0]) and abs(a[1] - b[1]) <= 1e-2 * abs(b[1]), (a, b)
+    assert runs[True]["host_enqueue_ms_per_step"] < 0.2 * runs[False]["host_enqueue_ms_per_step"]
+
+
 @pytest.mark.parametrize("R,K,N", [(50000, 128, 128), (40001, 64, 64), (33000, 3, 64), (20000, 131, 128), (12345, 260, 128),
                                    (30000, 128, 256), (9000, 256, 131), (5000, 64, 3), (70000, 128, 64), (2000, 128, 128),
                                    (8000, 256, 512)])
