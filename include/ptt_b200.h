@@ -315,6 +315,12 @@ PTT_API int ptt_tr_pair_inputs(const float* xyz, const int* knn, int B, int n, i
                        float* h1, float* delta, float* a_in, ptt_stream_t stream);
 /* dy <- dy * [ref > 0], count floats (multiple of 4), same layout */
 PTT_API int ptt_tr_mask_positive(float* dy, const float* ref, long long count, ptt_stream_t stream);
+/* out (R,d) = x (R,ldx)[:, 0:d] . W^T [* (mask_ref > 0)] for a square d x d layer (d = 256 or 512) over many rows: the
+ * persistent CTA-pair kernel of the block's forward passes with plain rows as the operand -- the pair-level input-gradient
+ * contractions of the backward (params = ptt_linear_pack_strided image of the (d,d) matrix, bias-free; mask_ref (R,d) or
+ * NULL = the ReLU backward against the stored activation, fused into the epilogue).  PTT_ERR_UNSUPPORTED for other d. */
+PTT_API int ptt_tr_rows_linear(const float* x, int ldx, long long R, int d, const float* params, const float* mask_ref_or_null,
+                       float* out, ptt_stream_t stream);
 /* da <- da + dvp (= dpos) in place; dq_i = sum_j da_ij; dk[knn] -= da; dv[knn] += dvp (atomics; zero dk / dv first) */
 PTT_API int ptt_tr_pair_scatter(float* da, const float* dvp, int ld, const int* knn, int B, int n, int k, int dm, float* dq,
                         float* dk, float* dv, int ldt, ptt_stream_t stream);

@@ -76,6 +76,7 @@ SIGNATURES = {
     "ptt_tr_softmax_bwd": (c_int, [_P, c_int, _P, _P, c_int, ctypes.c_longlong, c_int, c_int, c_float, _P, _P, _P]),
     "ptt_tr_pair_inputs": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P]),
     "ptt_tr_mask_positive": (c_int, [_P, _P, ctypes.c_longlong, _P]),
+    "ptt_tr_rows_linear": (c_int, [_P, c_int, ctypes.c_longlong, c_int, _P, _P, _P, _P]),
     "ptt_tr_pair_scatter": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P]),
     "ptt_mt19937_stream": (c_int, [ctypes.c_uint, c_int, _P]),
     "ptt_track_crop": (c_int, [c_int, c_int, _PP, _PP, _PP, _IP, _IP, ctypes.c_double, ctypes.c_double, c_int, _P, c_int, _P, _P]),
@@ -112,6 +113,10 @@ def lib():
             fn.argtypes = argtypes
         _lib = handle
     return _lib
+
+
+# return codes of include/ptt_b200.h
+PTT_OK, PTT_ERR_INVALID_ARGUMENT, PTT_ERR_UNSUPPORTED, PTT_ERR_WORKSPACE, PTT_ERR_DEVICE_FAULT = 0, -1, -2, -3, -4
 
 
 def check(code, what):

@@ -39,6 +39,9 @@ struct TrPassArgs {
   // column of TransformerBlockCosine's fc_sim pushed through fc_gamma.0
   const float* row_scalar = nullptr;   // (pairs)
   const float* col_vec = nullptr;      // (dm)
+  // STORE (transposed accumulators), optional: out <- out * [mask_ref > 0], mask_ref (pairs, dm) -- the ReLU backward of
+  // an input-gradient contraction against the stored activation (training path)
+  const float* mask_ref = nullptr;
 };
 
 bool tr_fused_supported(int n, int k, int dm);

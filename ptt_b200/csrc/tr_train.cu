@@ -9,6 +9,8 @@
 //   tr_pair_scatter                   dpos = da + d(v+pos);  dq_i = sum_j da_ij;  dk_j -= da_ij;  dv_j += d(v+pos)_ij  (atomics,
 //                                     like upstream's group_points_grad)
 #include "common.cuh"
+#include "gemm.cuh"
+#include "tr_fused.cuh"
 
 namespace {
 
@@ -218,4 +220,20 @@ extern "C" int ptt_tr_pair_scatter(float* da, const float* dvp, int ld, const in
   tr_pair_scatter_kernel<<<tt_grid(tokens * dm), TT, 0, as_stream(stream)>>>(da, dvp, ld, knn, n, k, dm, tokens, dq, dk, dv, ldt);
   PTT_LAUNCHED();
   return ptt_launch_status();
+}
+
+extern "C" int ptt_tr_rows_linear(const float* x, int ldx, long long R, int d, const float* params, const float* mask_ref,
+                                  float* out, ptt_stream_t stream) {
+  PTT_CHECK_ARG(R >= 0 && d >= 1 && ldx >= d);
+  if (R == 0) return PTT_OK;
+  PTT_CHECK_ARG(x && params && out);
+  if ((d != 256 && d != 512) || (ldx % 4) || (reinterpret_cast<uintptr_t>(x) & 15u)) return PTT_ERR_UNSUPPORTED;
+  TrPassArgs t;
+  t.n = 1; t.k = 1; t.dm = d; t.pairs = R;
+  t.a_src = x; t.lda = ldx;
+  t.wimg = params + (size_t)(d + 1) * ptt_linear_ldw(d);      // the fp16 hi/lo image inside the packed nn.Linear block
+  t.bias = nullptr;
+  t.out = out; t.ldo = d;
+  t.mask_ref = mask_ref;
+  return tr_fused_launch(t, TR_PROD_PLAIN, TR_EPI_STORE, as_stream(stream));
 }

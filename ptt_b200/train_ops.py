@@ -204,6 +204,26 @@ def _tr_layout(B, n, k, dp, dm):
     return [int(v) for v in out]
 
 
+def rows_linear_masked(packed, x, mask_ref=None):
+    """out (R, d) = x . W^T [* (mask_ref > 0)] for a packed bias-free square layer (ptt_tr_rows_linear: the persistent
+    CTA-pair kernel of the forward passes, ReLU backward fused into its epilogue); other shapes fall back to the generic
+    contraction + ptt_tr_mask_positive."""
+    R, d = x.shape[0], packed.cout
+    if packed.k == d and d in (256, 512) and not packed.has_bias and x.shape[1] % 4 == 0:
+        with _DeviceGuard(x.device):
+            out = torch.empty(R, d, dtype=_F, device=x.device)
+            rc = _lib.lib().ptt_tr_rows_linear(_ptr(x), x.shape[1], R, d, _ptr(packed.params), _ptr(mask_ref), _ptr(out), _stream())
+        if rc == 0:
+            return out
+        if rc != _lib.PTT_ERR_UNSUPPORTED:
+            check(rc, "ptt_tr_rows_linear")
+    out = packed(x)
+    if mask_ref is not None:
+        with _DeviceGuard(x.device):
+            check(_lib.lib().ptt_tr_mask_positive(_ptr(out), _ptr(mask_ref), out.numel(), _stream()), "ptt_tr_mask_positive")
+    return out
+
+
 class _TransformerTrain(torch.autograd.Function):
     """inputs: xyz (B,n,3), features (B,n,d_points), k, then the 15 parameters in ops.TRANSFORMER_KEYS order.
     Forward = the fused eval kernels (there is no BatchNorm in the block) with attn and a kept workspace; backward
@@ -261,10 +281,11 @@ class _TransformerTrain(torch.autograd.Function):
                                        _ptr(dvp), _stream()), "ptt_tr_softmax_bwd")
             # logits = fc_gamma.2(g), g = relu(fc_gamma.0(a_in))
             grads["fc_gamma.2.weight"], grads["fc_gamma.2.bias"] = linear_wgrad(dlogit, g, dm, dm, want_bias=True)
-            dpre = lin_t(W["fc_gamma.2.weight"])(dlogit)
-            check(L.ptt_tr_mask_positive(_ptr(dpre), _ptr(g), pairs * ld, _stream()), "ptt_tr_mask_positive")
+            dpre = rows_linear_masked(lin_t(W["fc_gamma.2.weight"]), dlogit, g if ld == dm else None)
+            if ld != dm:
+                check(L.ptt_tr_mask_positive(_ptr(dpre), _ptr(g), pairs * ld, _stream()), "ptt_tr_mask_positive")
             grads["fc_gamma.0.weight"], grads["fc_gamma.0.bias"] = linear_wgrad(dpre, a_in, dm, dm, want_bias=True)
-            da = lin_t(W["fc_gamma.0.weight"])(dpre)
+            da = rows_linear_masked(lin_t(W["fc_gamma.0.weight"]), dpre)
             # a_in = q_i - k_j + pos_ij ; vp = v_j + pos_ij
             dq = torch.empty(tokens, dm, dtype=_F, device=xyz.device)
             dk = torch.zeros(tokens, dm, dtype=_F, device=xyz.device)
@@ -274,8 +295,9 @@ class _TransformerTrain(torch.autograd.Function):
             dpos = da
             # pos = fc_delta.2(h1), h1 = relu(fc_delta.0(delta))
             grads["fc_delta.2.weight"], grads["fc_delta.2.bias"] = linear_wgrad(dpos, h1, dm, dm, want_bias=True)
-            dh1 = lin_t(W["fc_delta.2.weight"])(dpos)
-            check(L.ptt_tr_mask_positive(_ptr(dh1), _ptr(h1), pairs * ld, _stream()), "ptt_tr_mask_positive")
+            dh1 = rows_linear_masked(lin_t(W["fc_delta.2.weight"]), dpos, h1 if ld == dm else None)
+            if ld != dm:
+                check(L.ptt_tr_mask_positive(_ptr(dh1), _ptr(h1), pairs * ld, _stream()), "ptt_tr_mask_positive")
             grads["fc_delta.0.weight"], grads["fc_delta.0.bias"] = linear_wgrad(dh1, delta, dm, 3, want_bias=True)
             # q, k, v = W x ; x = fc1(features)
             grads["w_qs.weight"] = linear_wgrad(dq, x, dm, dm)
