@@ -87,33 +87,34 @@ __global__ void bn_train_finalize_kernel(const double* __restrict__ sums, long l
 
 // ---------------------------------------------------------------------------------------------- grouping
 // X0[(b, j, s), :] = [ (xyz[idx] - new_xyz[j]) (/ radius) | feats[idx, 0:C] | 0 pad ]   -- the reference's channel order
+template <typename I>   // I = unsigned when rows * ld / 4 < 2^32 (the 64-bit divisions are emulated: ~3x the instructions)
 __global__ void __launch_bounds__(TO_THREADS) sa_group_rows_kernel2(const float* __restrict__ xyz, const float* __restrict__ feats,
                                                                      int ldf, const float* __restrict__ new_xyz,
                                                                      const int* __restrict__ idx, int N, int M, int ns, int C,
                                                                      float radius, int normalize, long long rows,
                                                                      float* __restrict__ out, int ld) {
   // one thread per float4 of an output row (ld % 4 == 0): consecutive threads write consecutive 16-byte pieces
-  const unsigned q4 = (unsigned)ld / 4;
-  const long long total = rows * q4;
-  for (long long e = (long long)blockIdx.x * TO_THREADS + threadIdx.x; e < total; e += (long long)gridDim.x * TO_THREADS) {
-    const long long r = e / q4;
+  const I q4 = (I)(ld / 4);
+  const I total = (I)rows * q4;
+  for (I e = (I)blockIdx.x * TO_THREADS + threadIdx.x; e < total; e += (I)gridDim.x * TO_THREADS) {
+    const I r = e / q4;
     const int c0 = (int)(e - r * q4) * 4;
-    const long long cj = r / ns;                          // (b, j)
-    const long long b = cj / M;
-    const long long src = b * N + __ldg(idx + r);
+    const I cj = r / (I)ns;                               // (b, j)
+    const I b = cj / (I)M;
+    const size_t src = (size_t)b * N + __ldg(idx + r);
     float o[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int c = c0 + u;
       if (c < 3) {
-        float v = __fsub_rn(__ldg(xyz + src * 3 + c), __ldg(new_xyz + cj * 3 + c));
+        float v = __fsub_rn(__ldg(xyz + src * 3 + c), __ldg(new_xyz + (size_t)cj * 3 + c));
         if (normalize) v = __fdiv_rn(v, radius);
         o[u] = v;
       } else {
-        o[u] = c < 3 + C ? __ldg(feats + src * (long long)ldf + (c - 3)) : 0.f;
+        o[u] = c < 3 + C ? __ldg(feats + src * ldf + (c - 3)) : 0.f;
       }
     }
-    *reinterpret_cast<float4*>(out + r * ld + c0) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(out + (size_t)r * ld + c0) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -366,8 +367,14 @@ extern "C" int ptt_sa_group_rows(const float* xyz, const float* feats, int ldf, 
   const long long rows = (long long)B * M * ns;
   if (rows == 0) return PTT_OK;
   PTT_CHECK_ARG(xyz && new_xyz && idx && rows_out && (C == 0 || feats));
-  sa_group_rows_kernel2<<<grid_rows(rows * (ld / 4), TO_THREADS), TO_THREADS, 0, as_stream(stream)>>>(xyz, feats, ldf, new_xyz, idx, N, M, ns, C, radius,
-                                                                                 normalize_xyz, rows, rows_out, ld); PTT_LAUNCHED();
+  const int grid = grid_rows(rows * (ld / 4), TO_THREADS);
+  if (rows * (ld / 4) + (long long)grid * TO_THREADS < 0xffffffffLL)
+    sa_group_rows_kernel2<unsigned><<<grid, TO_THREADS, 0, as_stream(stream)>>>(xyz, feats, ldf, new_xyz, idx, N, M, ns, C, radius,
+                                                                              normalize_xyz, rows, rows_out, ld);
+  else
+    sa_group_rows_kernel2<unsigned long long><<<grid, TO_THREADS, 0, as_stream(stream)>>>(xyz, feats, ldf, new_xyz, idx, N, M, ns, C,
+                                                                                        radius, normalize_xyz, rows, rows_out, ld);
+  PTT_LAUNCHED();
   return ptt_launch_status();
 }
 
