@@ -281,6 +281,67 @@ __global__ void __launch_bounds__(TO_THREADS) bn_relu_bwd_apply_kernel(const BnB
   }
 }
 
+// POOLED form (the layer below the max over nsample): only the arg-max row of a (group, channel) carries gradient, so the
+// two sums need one y value per (group, channel) -- a gather of groups x C values instead of a pass over R x C --
+// and the apply pass walks a group's ns rows with its arg / dz loaded once (no per-row division, no per-row compare loads).
+__global__ void __launch_bounds__(TO_THREADS) bn_relu_bwd_pooled_reduce_kernel(const BnBwd p, double* __restrict__ sums) {
+  const BnChan ch = bn_chan(p, (threadIdx.x % (p.C / 4)) * 4);
+  column_reduce<2>(p.R / p.ns, p.C, sums, [&](long long g, int c, float (&acc)[2][4]) {
+    const int4 ai = __ldg(reinterpret_cast<const int4*>(p.arg + g * p.C + c));
+    const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dz + g * p.ldz + c));
+    const int a4[4] = {ai.x, ai.y, ai.z, ai.w};
+    const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float yv = __ldg(p.y + (g * p.ns + a4[u]) * p.ldy + c + u);
+      const float m = fmaf(yv, ch.a[u], ch.b[u]) > 0.f ? d4[u] : 0.f;
+      acc[0][u] += m;
+      acc[1][u] = fmaf(m, (yv - ch.mu[u]) * ch.rs[u], acc[1][u]);
+    }
+  });
+}
+
+// requires TO_THREADS % (C / 4) == 0: a thread keeps its 4 channels, TO_THREADS / (C / 4) groups per CTA and pass
+__global__ void __launch_bounds__(TO_THREADS) bn_relu_bwd_pooled_apply_kernel(const BnBwd p, const double* __restrict__ sums,
+                                                                               const float* __restrict__ gamma,
+                                                                               float* __restrict__ dy, int ld_dy,
+                                                                               float* __restrict__ dparam) {
+  if (dparam != nullptr && blockIdx.x == 0)
+    for (int c = threadIdx.x; c < 2 * p.C; c += TO_THREADS) dparam[c] = (float)sums[c];
+  const int tpr = p.C / 4;
+  const int c = (threadIdx.x % tpr) * 4;
+  const int gpp = TO_THREADS / tpr;
+  const double inv_r = 1.0 / (double)p.R;
+  const BnChan ch = bn_chan(p, c);
+  float gs[4], s1[4], s2[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    gs[u] = (gamma ? __ldg(gamma + c + u) : 1.f) * ch.rs[u];
+    s1[u] = (float)(sums[c + u] * inv_r);
+    s2[u] = (float)(sums[p.C + c + u] * inv_r);
+  }
+  const long long groups = p.R / p.ns;
+  for (long long g = (long long)blockIdx.x * gpp + threadIdx.x / tpr; g < groups; g += (long long)gridDim.x * gpp) {
+    const int4 ai = __ldg(reinterpret_cast<const int4*>(p.arg + g * p.C + c));
+    const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dz + g * p.ldz + c));
+    const float* yp = p.y + g * p.ns * p.ldy + c;
+    float* op = dy + g * p.ns * ld_dy + c;
+#pragma unroll 4
+    for (int s = 0; s < p.ns; ++s) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(yp + (long long)s * p.ldy));
+      const float yv[4] = {v.x, v.y, v.z, v.w};
+      const float d4[4] = {ai.x == s ? dv.x : 0.f, ai.y == s ? dv.y : 0.f, ai.z == s ? dv.z : 0.f, ai.w == s ? dv.w : 0.f};
+      float o[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float m = fmaf(yv[u], ch.a[u], ch.b[u]) > 0.f ? d4[u] : 0.f;
+        o[u] = gs[u] * (m - s1[u] - (yv[u] - ch.mu[u]) * ch.rs[u] * s2[u]);
+      }
+      *reinterpret_cast<float4*>(op + (long long)s * ld_dy) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 int grid_rows(long long work, int per_block) {
   long long b = (work + per_block - 1) / per_block;
   return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
@@ -415,6 +476,13 @@ extern "C" int ptt_bn_relu_bwd(const float* dz, int ldz, const int* argmax_or_nu
   BnBwd p;
   p.dz = dz; p.ldz = ldz; p.arg = argmax_or_null; p.ns = ns; p.y = y; p.ldy = ldy;
   p.ka = ka; p.kb = kb; p.mean = mean; p.rstd = rstd; p.R = R; p.C = C;
+  if (argmax_or_null != nullptr && R % ns == 0 && TO_THREADS % (C / 4) == 0) {
+    const long long groups = R / ns;
+    bn_relu_bwd_pooled_reduce_kernel<<<grid_rows(groups, 16), TO_THREADS, 0, st>>>(p, sums); PTT_LAUNCHED();
+    bn_relu_bwd_pooled_apply_kernel<<<grid_rows(groups * (C / 4), TO_THREADS), TO_THREADS, 0, st>>>(p, sums, gamma, dy, ld_dy,
+                                                                                                  dparam_or_null); PTT_LAUNCHED();
+    return ptt_launch_status();
+  }
   bn_relu_bwd_reduce_kernel<<<grid_rows(R, 64), TO_THREADS, 0, st>>>(p, sums); PTT_LAUNCHED();
   bn_relu_bwd_apply_kernel<<<grid_rows(R * (C / 4), TO_THREADS), TO_THREADS, 0, st>>>(p, sums, gamma, dy, ld_dy, dparam_or_null); PTT_LAUNCHED();
   return ptt_launch_status();
