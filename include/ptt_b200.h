@@ -190,6 +190,16 @@ PTT_API int ptt_linear_pack(const float* weight, const float* bias, int K, int C
  * transposed weight of an input-gradient contraction is ld_c = 1, ld_k = its row length -- no transposed copy). */
 PTT_API int ptt_linear_pack_strided(const float* weight, long long ld_c, long long ld_k, const float* bias, int K, int Cout,
                             float* params, ptt_stream_t stream);
+/* Many layers in ONE launch (a training step repacks every layer after the optimiser update): `descs_device` is a DEVICE
+ * array of `count` descriptors; every entry is packed as ptt_linear_pack_strided would pack it. */
+typedef struct PttPackDesc {
+  const float* weight;       /* W[c, k] = weight[c * ld_c + k * ld_k] */
+  long long ld_c, ld_k;
+  const float* bias;         /* Cout floats or NULL */
+  float* params;             /* ptt_linear_params_floats(K, Cout) floats */
+  int K, Cout;
+} PttPackDesc;
+PTT_API int ptt_linear_pack_batch(const PttPackDesc* descs_device, int count, ptt_stream_t stream);
 PTT_API int ptt_linear_fwd(const float* x, int ldx, int R, int K, const float* params, int Cout, int relu,
                    const float* residual, int ldr, float* y, int ldy, ptt_stream_t stream);
 

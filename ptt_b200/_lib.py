@@ -48,6 +48,7 @@ SIGNATURES = {
     "ptt_linear_params_floats": (c_size_t, [c_int, c_int]),
     "ptt_linear_pack": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "ptt_linear_pack_strided": (c_int, [_P, ctypes.c_longlong, ctypes.c_longlong, _P, c_int, c_int, _P, _P]),
+    "ptt_linear_pack_batch": (c_int, [_P, c_int, _P]),
     "ptt_linear_fwd": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, _P]),
     "ptt_transformer_params_floats": (c_size_t, [c_int, c_int]),
     "ptt_transformer_pack_params": (c_int, [c_int, c_int] + [_P] * 15 + [_P, _P]),

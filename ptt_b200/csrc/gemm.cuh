@@ -47,6 +47,8 @@ int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout,
 // nn.Linear image of ptt_linear_pack (transposed fp32 weight, bias row, fp16 image) from a strided source, one launch
 int ptt_linear_pack_all(const float* w, long long ld_c, long long ld_k, const float* bias, int K, int Cout, float* params,
                         cudaStream_t st);
+// the same for `count` layers described by a DEVICE table (include/ptt_b200.h: PttPackDesc), one launch
+int ptt_linear_pack_batch_launch(const PttPackDesc* descs_device, int count, cudaStream_t st);
 bool ptt_tc_gemm_supported(const PttGemmArgs& a);
 int ptt_tc_gemm_launch(const PttGemmArgs& a, const void* wimg, cudaStream_t st);
 // floats occupied by the tcgen05 image of a (Cout, K) weight

@@ -173,6 +173,11 @@ extern "C" int ptt_linear_pack_strided(const float* weight, long long ld_c, long
   return ptt_linear_pack_all(weight, ld_c, ld_k, bias, K, Cout, params, as_stream(stream));
 }
 
+extern "C" int ptt_linear_pack_batch(const PttPackDesc* descs_device, int count, ptt_stream_t stream) {
+  PTT_CHECK_ARG(count >= 0 && count <= 65535 && (count == 0 || descs_device != nullptr));
+  return ptt_linear_pack_batch_launch(descs_device, count, as_stream(stream));
+}
+
 extern "C" int ptt_linear_fwd(const float* x, int ldx, int R, int K, const float* params, int Cout, int relu,
                               const float* residual, int ldr, float* y, int ldy, ptt_stream_t stream) {
   PTT_CHECK_ARG(R >= 0 && K >= 1 && Cout >= 1 && ldx >= K && ldy >= Cout);

@@ -327,6 +327,38 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, long long ld_
   }
 }
 
+// Many layers in one launch: blockIdx.y = layer, its descriptor read from a device table (the training step repacks ~70
+// layers per step; one 5 us launch instead of 70)
+__global__ void tc_pack_batch_kernel(const PttPackDesc* __restrict__ descs) {
+  const PttPackDesc d = descs[blockIdx.y];
+  const float* __restrict__ w = d.weight;
+  const int K = d.K, Cout = d.Cout, ldw = (Cout + 3) & ~3;       // = ptt_linear_ldw(Cout)
+  const int NB = (Cout + 63) / 64, KB = (K + 63) / 64;
+  float* wt = d.params;
+  __half* img = reinterpret_cast<__half*>(d.params + (size_t)(K + 1) * ldw);
+  const int total_t = (K + 1) * ldw;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total_t; e += gridDim.x * blockDim.x) {
+    const int k = e / ldw, c = e - k * ldw;
+    wt[e] = c < Cout ? (k < K ? w[(long long)c * d.ld_c + (long long)k * d.ld_k] : (d.bias ? d.bias[c] : 0.f)) : 0.f;
+  }
+  const int total = NB * KB * 512;   // (block, row, chunk)
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int c = e & 7, r = (e >> 3) & 63, blk = e >> 9;
+    const int kb = blk % KB, nb = blk / KB;
+    const int n = nb * 64 + r;
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = kb * 64 + c * 8 + u;
+      const float x = (n < Cout && k < K) ? w[(long long)n * d.ld_c + (long long)k * d.ld_k] : 0.f;
+      tc::split_f16(x, hi[u], lo[u]);
+    }
+    uint8_t* base = reinterpret_cast<uint8_t*>(img) + (size_t)blk * 2 * W_BLOCK_BYTES + tc::sw128_offset(r, c);
+    *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + W_BLOCK_BYTES) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 template <int BN>
 int tc_launch(const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
@@ -357,6 +389,12 @@ int ptt_tc_pack_weight(const float* w, long long ld_c, long long ld_k, int Cout,
   dim3 grid((unsigned)llmin_((total + 255) / 256, 2048), batch > 0 ? batch : 1);
   tc_pack_weight_kernel<<<grid, 256, 0, st>>>(w, ld_c, ld_k, Cout, K, NB, KB, row_scale, static_cast<__half*>(img), w_bstride,
                                               img_bstride, nullptr, 0, nullptr); PTT_LAUNCHED();
+  return ptt_launch_status();
+}
+
+int ptt_linear_pack_batch_launch(const PttPackDesc* descs_device, int count, cudaStream_t st) {
+  if (count <= 0) return PTT_OK;
+  tc_pack_batch_kernel<<<dim3(32, (unsigned)count), 256, 0, st>>>(descs_device); PTT_LAUNCHED();
   return ptt_launch_status();
 }
 

@@ -48,6 +48,9 @@ class HotPathNet(nn.Module):
         self.npoints_search, self.npoints_template, self.box_npoint = npoints_search, npoints_template, box_npoint
 
     def forward(self, search, template):
+        if self.training:
+            from . import train_ops
+            train_ops.repack_stale(self.modules())       # every layer's packed images after the optimiser update: one launch
         s_xyz, s_feat = self.backbone_3d(search, self.npoints_search)
         t_xyz, t_feat = self.backbone_3d(template, self.npoints_template)
         cen, _ = self.centroid_voting_head.transformer_block(s_xyz, s_feat.transpose(1, 2).contiguous())

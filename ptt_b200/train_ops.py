@@ -12,6 +12,7 @@ apply relu(ka * y + kb) while loading y_l.  Saved for backward: the grouped inpu
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from . import _lib, ops
@@ -108,12 +109,85 @@ def bn_relu_bwd(dz, argmax, ns, y, C, ka, kb, mean, rstd, gamma):
     return dy, sums, dparam
 
 
+class TrainPacks:
+    """Per-module cache of the packed weight images the native training path consumes (the layer's weight for the forward
+    contraction, its transpose for the input gradient).  An image is valid while the parameter's `_version` and address
+    are the ones it was packed from: `get` repacks a stale image with one launch, `repack_stale` refreshes the stale images
+    of MANY modules with ONE launch (ptt_linear_pack_batch) -- a training step calls it once after the optimiser update."""
+
+    def __init__(self):
+        self.entries = {}
+
+    @staticmethod
+    def _ver(weight, bias):
+        return (weight._version, weight.data_ptr(), -1 if bias is None else bias._version, 0 if bias is None else bias.data_ptr())
+
+    @staticmethod
+    def _src(weight, shape2d, transposed):
+        w2 = weight.detach().reshape(shape2d)
+        return w2.t() if transposed else w2
+
+    def get(self, key, weight, shape2d, transposed=False, bias=None):
+        ver = self._ver(weight, bias)
+        ent = self.entries.get(key)
+        if ent is None or ent["shape"] != tuple(shape2d):
+            packed = ops.PackedLinear(self._src(weight, shape2d, transposed), None if bias is None else bias.detach(), check_range=False)
+            ent = {"packed": packed, "shape": tuple(shape2d), "t": bool(transposed)}
+            self.entries[key] = ent
+        elif ent["ver"] != ver:
+            ent["packed"].repack(self._src(weight, shape2d, transposed), None if bias is None else bias.detach())
+        ent["ver"], ent["weight"], ent["bias"] = ver, weight, bias
+        return ent["packed"]
+
+
+_DESC = np.dtype([("w", "<u8"), ("ld_c", "<i8"), ("ld_k", "<i8"), ("b", "<u8"), ("p", "<u8"), ("K", "<i4"), ("C", "<i4")])   # PttPackDesc
+_TABLES = {}          # (device, descriptor bytes) -> device copy of the table (a step's set of stale layers repeats every step)
+
+
+def repack_stale(modules):
+    """Refresh, with one launch, every stale image of the `train_packs` caches of `modules` (no-op while fewer than two are
+    stale; the per-image path of TrainPacks.get handles whatever this leaves)."""
+    stale = []
+    for m in modules:
+        packs = getattr(m, "train_packs", None)
+        if packs is None:
+            continue
+        for ent in packs.entries.values():
+            if ent["ver"] != TrainPacks._ver(ent["weight"], ent["bias"]):
+                stale.append(ent)
+    if len(stale) < 2:
+        return 0
+    dev = stale[0]["weight"].device
+    desc = np.zeros(len(stale), dtype=_DESC)
+    for i, ent in enumerate(stale):
+        w, cout, k = ent["weight"], ent["packed"].cout, ent["packed"].k
+        rows, cols = ent["shape"]                              # the (rows, cols) matrix the parameter is viewed as
+        desc[i] = ((w.data_ptr(), 1, cols, 0, 0, k, cout) if ent["t"] else (w.data_ptr(), cols, 1, 0, 0, k, cout))
+        desc[i]["b"] = 0 if ent["bias"] is None else ent["bias"].data_ptr()
+        desc[i]["p"] = ent["packed"].params.data_ptr()
+    key = (str(dev), desc.tobytes())
+    table = _TABLES.get(key)
+    if table is None:
+        if torch.cuda.is_current_stream_capturing():
+            return 0                                           # no host -> device copy inside a capture; the per-image path runs
+        if len(_TABLES) > 64:
+            _TABLES.clear()
+        table = torch.from_numpy(desc.view(np.uint8).copy()).to(dev)
+        _TABLES[key] = table
+    with _DeviceGuard(dev):
+        check(_lib.lib().ptt_linear_pack_batch(_ptr(table), len(stale), _stream()), "ptt_linear_pack_batch")
+    for ent in stale:
+        ent["packed"].has_bias = ent["bias"] is not None
+        ent["ver"] = TrainPacks._ver(ent["weight"], ent["bias"])
+    return len(stale)
+
+
 class _SATrain(torch.autograd.Function):
     """inputs: xyz (B,N,3), feats_cm (B,C,N) | None, new_xyz (B,M,3), idx (B,M,ns) int32, then per layer
     (conv weight (Cout,Cin,1,1), bn weight, bn bias, running_mean, running_var)."""
 
     @staticmethod
-    def forward(ctx, xyz, feats_cm, new_xyz, idx, radius, normalize, eps, momentum, *params):
+    def forward(ctx, xyz, feats_cm, new_xyz, idx, radius, normalize, eps, momentum, packs, *params):
         L = len(params) // 5
         B, N, _ = xyz.shape
         _, M, ns = idx.shape
@@ -126,7 +200,7 @@ class _SATrain(torch.autograd.Function):
         for l in range(L):
             w, g, b, rm, rv = params[5 * l: 5 * l + 5]
             cout = w.shape[0]
-            lin = ops.PackedLinear(w.detach().reshape(cout, k_in).contiguous(), None, check_range=False)
+            lin = packs.get((l, "fwd"), w, (cout, k_in))
             y, sums = ops.linear_with_stats(lin, src, in_affine=aff)      # the statistics come out of the contraction's epilogue
             ka, kb, mean, rstd = bn_train_finalize(sums, R, g.detach(), b.detach(), eps, momentum, rm, rv)
             ys.append(y)
@@ -137,6 +211,7 @@ class _SATrain(torch.autograd.Function):
         ctx.save_for_backward(x0, idx, arg, *ys, *[t for a in affs for t in a], *[t for s in stats for t in s],
                               *[params[5 * l].detach() for l in range(L)], *[params[5 * l + 1].detach() for l in range(L)])
         ctx.meta = (L, B, N, M, ns, C, float(radius), bool(normalize))
+        ctx.packs = packs
         ctx.mark_non_differentiable(arg)
         return ops.pm_to_cm(out.view(B, M, k_in)), arg
 
@@ -164,7 +239,7 @@ class _SATrain(torch.autograd.Function):
             grads[5 * l] = linear_wgrad(dy, src, cout, cin, aff).reshape(ws[l].shape)
             need_dx = l > 0 or ctx.needs_input_grad[0] or (C > 0 and ctx.needs_input_grad[1]) or ctx.needs_input_grad[2]
             if need_dx:
-                wt = ops.PackedLinear(ws[l].reshape(cout, cin).t(), None, check_range=False)   # strided pack: no transposed copy
+                wt = ctx.packs.get((l, "dgrad"), ws[l], (cout, cin), transposed=True)   # strided pack: no transposed copy
                 # padded rows only below layer 0, where ptt_sa_group_rows_grad reads the first 3 + C columns and nothing else
                 dz, _ = ops.linear_with_stats(wt, dy, want_stats=False, ld_out=_pad4(cin), zero_pad=False)
         d_xyz = d_feats = d_new = None
@@ -173,7 +248,7 @@ class _SATrain(torch.autograd.Function):
             d_feats_pm, d_xyz, d_new = sa_group_rows_grad(dz, idx, N, C, radius, normalize, C > 0 and ctx.needs_input_grad[1], want_xyz)
             if d_feats_pm is not None:
                 d_feats = ops.pm_to_cm(d_feats_pm, C)
-        return (d_xyz, d_feats, d_new, None, None, None, None, None, *grads)
+        return (d_xyz, d_feats, d_new, None, None, None, None, None, None, *grads)
 
 
 def sa_train(xyz, feats_cm, new_xyz, idx, radius, normalize, mlp_module):
@@ -190,7 +265,10 @@ def sa_train(xyz, feats_cm, new_xyz, idx, radius, normalize, mlp_module):
             raise PttError("sa_train: the BatchNorm layers of one SharedMLP share eps / momentum")
         params += [unit.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
         bn.num_batches_tracked += 1
-    out, _ = _SATrain.apply(xyz, feats_cm, new_xyz, idx, float(radius), bool(normalize), float(eps), float(momentum), *params)
+    if getattr(mlp_module, "train_packs", None) is None:
+        mlp_module.train_packs = TrainPacks()
+    out, _ = _SATrain.apply(xyz, feats_cm, new_xyz, idx, float(radius), bool(normalize), float(eps), float(momentum),
+                            mlp_module.train_packs, *params)
     return out
 
 
@@ -231,7 +309,7 @@ class _TransformerTrain(torch.autograd.Function):
     the input / weight gradient contractions on tcgen05 (ptt_linear_fwd, ptt_linear_wgrad)."""
 
     @staticmethod
-    def forward(ctx, xyz, features, k, *params):
+    def forward(ctx, xyz, features, k, packs, *params):
         sd = {key: p.detach() for key, p in zip(ops.TRANSFORMER_KEYS, params)}
         packed = ops.PackedTransformer(sd, k, check_range=False)
         B, n, dp = features.shape
@@ -241,6 +319,7 @@ class _TransformerTrain(torch.autograd.Function):
         out, attn = ops.transformer_block_fwd(packed, xyz, features, knn_idx=knn, want_attn=True, workspace=ws)
         ctx.save_for_backward(xyz, features, knn, attn, ws, *[p.detach() for p in params])
         ctx.meta = (B, n, int(k), dp, packed.d_model)
+        ctx.packs = packs
         ctx.mark_non_differentiable(attn)
         return out, attn
 
@@ -256,8 +335,9 @@ class _TransformerTrain(torch.autograd.Function):
         res = ws[off[3]: off[3] + tokens * ld].view(tokens, ld)
         g = ws[off[4]: off[4] + pairs * ld].view(pairs, ld)
         vp = ws[off[5]: off[5] + pairs * ld].view(pairs, ld)
-        lin = lambda w, b=None: ops.PackedLinear(w, b, check_range=False)
-        lin_t = lambda w: ops.PackedLinear(w.t(), None, check_range=False)      # strided pack: no transposed copy
+        names = {id(t): key for key, t in W.items()}
+        lin = lambda w, b=None: ctx.packs.get((names[id(w)], "fwd"), w, tuple(w.shape), bias=b)
+        lin_t = lambda w: ctx.packs.get((names[id(w)], "dgrad"), w, tuple(w.shape), transposed=True)   # strided: no transposed copy
         f2 = features.reshape(tokens, dp)
         dout2 = dout.reshape(tokens, dp).contiguous()
         # token-level projections, recomputed (tokens x d_model each)
@@ -308,7 +388,7 @@ class _TransformerTrain(torch.autograd.Function):
             dx = lin_t(W["w_vs.weight"])(dv, residual=dx)
             grads["fc1.weight"], grads["fc1.bias"] = linear_wgrad(dx, f2, dm, dp, want_bias=True)
             df = lin_t(W["fc1.weight"])(dx, residual=dout2)
-        return (None, df.view(B, n, dp), None, *[grads[key].contiguous() for key in ops.TRANSFORMER_KEYS])
+        return (None, df.view(B, n, dp), None, None, *[grads[key].contiguous() for key in ops.TRANSFORMER_KEYS])
 
 
 def transformer_train_supported(block, xyz, features):
@@ -320,4 +400,6 @@ def transformer_train_supported(block, xyz, features):
 def transformer_train(block, xyz, features):
     """TransformerBlock.forward in train() mode on the native path -> (res, attn)."""
     params = [dict(block.named_parameters())[key] for key in ops.TRANSFORMER_KEYS]
-    return _TransformerTrain.apply(xyz, features, block.k, *params)
+    if getattr(block, "train_packs", None) is None:
+        block.train_packs = TrainPacks()
+    return _TransformerTrain.apply(xyz, features, block.k, block.train_packs, *params)

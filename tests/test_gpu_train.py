@@ -252,6 +252,31 @@ def test_rows_linear_masked_vs_torch(R, d):
     close(train_ops.rows_linear_masked(packed, x, ref), want * (ref > 0), 2e-5, "masked")
 
 
+def test_batched_repack_equals_per_layer_packs():
+    """train_ops.repack_stale: after an in-place parameter update every cached image (forward and transposed) is refreshed
+    by ONE ptt_linear_pack_batch launch and equals a fresh per-layer pack."""
+    from ptt_b200 import train
+    net = train.HotPathNet()
+    synth.load_filled(net, seed=0)
+    net = net.to(DEV).train()
+    search = torch.from_numpy(synth.make_clouds(2, 1024, 810, "dense")).to(DEV)
+    template = torch.from_numpy(synth.make_clouds(2, 512, 811, "dense", role="template")).to(DEV)
+    sum((v.float() ** 2).mean() for v in net(search, template).values()).backward()      # creates the caches
+    mods = [m for m in net.modules() if getattr(m, "train_packs", None) is not None]
+    n_entries = sum(len(m.train_packs.entries) for m in mods)
+    assert len(mods) >= 5 and n_entries >= 40
+    assert train_ops.repack_stale(net.modules()) == 0, "nothing is stale right after the step"
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.25).add_(0.01)                                                      # what an optimiser step does
+    assert train_ops.repack_stale(net.modules()) == n_entries
+    for m in mods:
+        for ent in m.train_packs.entries.values():
+            w2 = ent["weight"].detach().reshape(ent["shape"])
+            fresh = ops.PackedLinear(w2.t() if ent["t"] else w2, None if ent["bias"] is None else ent["bias"].detach(), check_range=False)
+            assert torch.equal(ent["packed"].params, fresh.params)
+
+
 def test_train_step_cuda_graph_replay_matches_eager_steps():
     """train.time_train_step: the whole step (forward, backward, clipping, Adam) captured once and replayed must follow the
     same loss trajectory as eager launches of the same step (the split-K atomics are the only unordered arithmetic)."""
