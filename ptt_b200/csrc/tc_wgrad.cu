@@ -20,6 +20,7 @@
 // while the rows are staged (BatchNorm + ReLU of the training path), so normalised activations are never stored.
 #include "gemm.cuh"
 #include "tc_common.cuh"
+#include <cmath>
 
 namespace {
 
@@ -311,6 +312,14 @@ int wg_launch(WgArgs a, int ntiles_n, cudaStream_t st) {
   const int tiles_mn = tiles_m * ntiles_n;
   const long long kblocks = (a.R + KBR - 1) / KBR;
   int nsplit = (int)llmin_(kblocks, (long long)((2 * sms + tiles_mn - 1) / tiles_mn));   // ~2 waves of CTAs
+  // ... unless the rows are few: every CTA adds its whole tile to dW with atomics, so the split costs nsplit x M x N reductions
+  // (~1.6e11 floats/s with 16-byte vector reductions) against (k-blocks / nsplit) x ~1.5 us of staging per CTA; the sum is
+  // smallest at nsplit^2 = k-blocks x 2.4e5 / (tiles x tile size).  (A 6144-row, 512 x 256 gradient: 48 -> 13 CTAs per tile.)
+  {
+    const double tile_elems = (double)tiles_mn * (MT * 128) * (NT * 64);
+    const int best = (int)(sqrt((double)kblocks * 2.4e5 / tile_elems) + 0.5);
+    if (best < nsplit) nsplit = best;
+  }
   if (nsplit < 1) nsplit = 1;
   a.rows_per_cta = ((kblocks + nsplit - 1) / nsplit) * KBR;
   nsplit = (int)((a.R + a.rows_per_cta - 1) / a.rows_per_cta);
