@@ -156,6 +156,9 @@ def time_train_step(device, world=1, rank=0, local_rank=0, batch=48, steps=5, wa
     host_ms = (time.perf_counter() - t0) * 1e3 / steps                  # host time to ENQUEUE a step (no synchronisation inside)
     e1.record()
     torch.cuda.synchronize(device)
+    if g is not None:
+        from . import train_ops
+        train_ops.invalidate_packs(net.modules())     # replays moved the parameters behind the caches' back (see its docstring)
     in_sync = None
     if world > 1:
         # the DDP invariant after the timed steps: every rank holds bit-identical parameters (the all-reduce -- captured

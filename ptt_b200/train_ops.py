@@ -140,6 +140,17 @@ class TrainPacks:
         return ent["packed"]
 
 
+def invalidate_packs(modules):
+    """Mark every cached image of `modules` stale.  Needed after CUDA-graph REPLAYS of a training step: a replay updates the
+    parameters on the device without touching their Python-side `_version`, so the caches cannot see that the images of the
+    last replay were packed from the parameters BEFORE its optimiser update."""
+    for m in modules:
+        packs = getattr(m, "train_packs", None)
+        if packs is not None:
+            for ent in packs.entries.values():
+                ent["ver"] = None
+
+
 _DESC = np.dtype([("w", "<u8"), ("ld_c", "<i8"), ("ld_k", "<i8"), ("b", "<u8"), ("p", "<u8"), ("K", "<i4"), ("C", "<i4")])   # PttPackDesc
 _TABLES = {}          # (device, descriptor bytes) -> device copy of the table (a step's set of stale layers repeats every step)
 

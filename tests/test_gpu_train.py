@@ -275,6 +275,8 @@ def test_batched_repack_equals_per_layer_packs():
             w2 = ent["weight"].detach().reshape(ent["shape"])
             fresh = ops.PackedLinear(w2.t() if ent["t"] else w2, None if ent["bias"] is None else ent["bias"].detach(), check_range=False)
             assert torch.equal(ent["packed"].params, fresh.params)
+    train_ops.invalidate_packs(net.modules())                 # what a caller does after CUDA-graph replays of the step
+    assert train_ops.repack_stale(net.modules()) == n_entries
 
 
 def test_train_step_cuda_graph_replay_matches_eager_steps():
