@@ -474,7 +474,7 @@ class HostPipeline:
 
     depth: 2 is the smallest that overlaps anything; 3 measured +3 % device-resident and +8 % end to end at batch 48 (the
     third slot's copies hide completely under the other two's kernels; bench.py uses 3), 4 adds < 1 %.  Each slot owns a
-    full set of workspaces (~0.6 GB at batch 48)."""
+    full set of workspaces and result buffers."""
 
     def __init__(self, state_dict, cfg=None, device="cuda", depth=2, outputs=None, full=False):
         self.slots = [HotPath(state_dict, cfg=cfg, device=device) for _ in range(depth)]
