@@ -5,7 +5,7 @@
  * stream) or an entry point that runs one kernel variant the product dispatcher would not pick.  The
  * parity tests use them to run every variant of a kernel family against the oracle
  * (tests/test_gpu_ops.py, tests/test_gpu_modules.py) and the tools/ scripts to record timelines.
- * Product code (ptt_b200/*.py) never calls them; ptt_b200.h's contract holds as long as they are left alone.
+ * Product code (the Python files of ptt_b200) never calls them; ptt_b200.h's contract holds as long as they are left alone.
  */
 #ifndef PTT_B200_TUNING_H_
 #define PTT_B200_TUNING_H_

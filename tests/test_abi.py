@@ -74,6 +74,27 @@ def test_tuning_surface_is_declared_bound_and_unused_by_the_product(built_lib):
             assert name not in text, "%s uses the tuning hook %s" % (path, name)
 
 
+def test_headers_are_plain_c_and_the_pack_descriptor_layout_matches_the_binding(tmp_path):
+    """include/*.h must compile as C99 (what a cgo / JNI / ctypes binding sees), and the device descriptor table that
+    ptt_b200/train_ops.py builds with numpy for ptt_linear_pack_batch must have the C struct's size and field offsets."""
+    import shutil
+    import subprocess
+
+    from ptt_b200 import train_ops
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ptt_b200.h"\n#include "ptt_b200_tuning.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PttPackDesc), offsetof(PttPackDesc, weight), '
+                   'offsetof(PttPackDesc, ld_c), offsetof(PttPackDesc, ld_k), offsetof(PttPackDesc, bias), offsetof(PttPackDesc, params), '
+                   'offsetof(PttPackDesc, K), offsetof(PttPackDesc, Cout)); return 0; }\n')
+    exe = tmp_path / "hdr"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    d = train_ops._DESC
+    assert got == [d.itemsize] + [d.fields[n][1] for n in ("w", "ld_c", "ld_k", "b", "p", "K", "C")]
+
+
 def test_fault_word_is_quiet_without_a_device(built_lib):
     from ptt_b200 import _lib
     assert _lib.fault_status() == 0          # never allocates, never touches CUDA
