@@ -6,8 +6,9 @@
 
 One rank per GPU; every rank trains on its own 48 synthetic frames per step (weak scaling).  A step = forward in train()
 mode (BatchNorm batch statistics), a synthetic L2 loss on the block outputs, backward, DDP gradient all-reduce over NCCL
-(the ONLY collective of the step) and an SGD update.  Timed on the device with CUDA events, max over ranks; rank 0 prints
-one JSON line.  The training arithmetic is the reference's decomposition over our CUDA ops (ptt_b200/train.py)."""
+(the ONLY collective of the step), clip_grad_norm_(10) and an Adam update, all on the native kernels (ptt_b200/train_ops.py).
+By default the whole step is captured once into a CUDA graph and the timed steps are replays (ptt_b200/train.py);
+--eager times plain launches.  Timed on the device with CUDA events, max over ranks; rank 0 prints one JSON line."""
 import argparse
 import json
 import os
