@@ -2,9 +2,11 @@
 backbone SA1-3 + cov_final (pointnet2_backbone.py:14-50), the two transformer blocks and the box-head SA
 (centroids_voting_head.py:27-28, box_voting_head.py:15-31) -- assembled from ptt_b200.modules with the reference's
 parameter names, so that `state_dict()` keys are those HotPath consumes and a reference checkpoint's hot-path entries
-load by key.  In train() mode every module runs the reference's decomposition over our CUDA ops under autograd
-(BatchNorm batch statistics, gradients as in the reference); under DistributedDataParallel the only collective of a
-step is the gradient all-reduce over NCCL.
+load by key.  In train() mode the SA layers and transformer blocks run the NATIVE training Functions of
+ptt_b200/train_ops.py (forward and backward are library kernels; BatchNorm batch statistics and gradients as in the
+reference; `module.native_train = False` selects the reference's decomposition over our ops under autograd, the
+cross-check of the tests); under DistributedDataParallel the only collective of a step is the gradient all-reduce over
+NCCL.  `time_train_step` is the step bench.py reports: by default captured once into a CUDA graph and replayed.
 """
 import torch
 import torch.nn as nn
