@@ -6,9 +6,11 @@
 //
 //   reference                                                       here
 //   QueryAndGroup + cat (pointnet2_utils.py:320-380)                sa_group_rows(_grad)
-//   Conv2d 1x1 -> BatchNorm2d(train) -> ReLU (pytorch_utils.py)     tc_gemm + col_stats + bn_train_finalize (two-phase)
+//   Conv2d 1x1 -> BatchNorm2d(train) -> ReLU (pytorch_utils.py)     ws_gemm (statistics in its epilogue; else tc_gemm +
+//                                                                   col_stats) + bn_train_finalize (two-phase)
 //   F.max_pool2d over nsample (pointnet2_modules.py:85)             bn_relu_maxpool (+ the first-max index for backward)
-//   autograd of BatchNorm / ReLU / max_pool                         bn_relu_bwd_reduce + bn_relu_bwd_apply
+//   autograd of BatchNorm / ReLU / max_pool                         bn_relu_bwd_reduce + bn_relu_bwd_apply (dense),
+//                                                                   bn_relu_bwd_pooled_* (below the max: arg-max rows only)
 #include "gemm.cuh"
 
 namespace {
